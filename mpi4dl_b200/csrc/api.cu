@@ -1,0 +1,211 @@
+// api.cu -- C-ABI entry points for convolution (include/spconv.h) and algorithm dispatch.
+//
+// Dispatch: shapes the tcgen05 implicit-GEMM path supports (gemm_tc.cu) run there over the
+// whole tile with zero padding; if the tile has neighbours, the thin output strips whose
+// receptive field reaches into a halo are then recomputed by the direct kernel, which reads the
+// received strips in place.  Interior compute therefore never waits on the halo exchange --
+// the overlap the reference left as dead code (spatial.py:415-866).  Everything else runs
+// entirely on the direct kernel.
+#include "common.cuh"
+
+namespace spc {
+namespace {
+
+int validate(const spc_conv_desc* d) {
+  SPC_REQUIRE(d != nullptr, "conv: null descriptor");
+  SPC_REQUIRE(d->N >= 0 && d->C > 0 && d->K > 0 && d->H > 0 && d->W > 0, "conv: bad shape N=%d C=%d K=%d H=%d W=%d",
+              d->N, d->C, d->K, d->H, d->W);
+  SPC_REQUIRE(d->R >= 1 && d->S >= 1 && d->stride_h >= 1 && d->stride_w >= 1, "conv: bad filter/stride");
+  // reference spatial.py:115-121: halo_len = (k-1)/2 must equal the conv padding ("same")
+  SPC_REQUIRE(d->pad_h == (d->R - 1) / 2 && d->pad_w == (d->S - 1) / 2,
+              "conv: Spatial not supported yet for this configuration (pad (%d,%d) != ((R-1)/2,(S-1)/2) for %dx%d)",
+              d->pad_h, d->pad_w, d->R, d->S);
+  SPC_REQUIRE(d->dtype == SPC_F32 || d->dtype == SPC_BF16, "conv: bad dtype %d", d->dtype);
+  SPC_REQUIRE(d->pad_h <= d->H && d->pad_w <= d->W, "conv: halo larger than the tile");
+  return SPC_OK;
+}
+
+bool has_halo(const spc_halo* h) {
+  if (!h) return false;
+  for (int i = 0; i < 9; ++i)
+    if (i != 4 && h->strip[i]) return true;
+  return false;
+}
+
+DirectConvParams fwd_params(const spc_conv_desc* d, const void* x, const spc_halo* halo, const void* w,
+                            const void* bias, void* y) {
+  DirectConvParams p{};
+  p.in = make_view(x, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);
+  p.w = w; p.bias = bias; p.y = y;
+  p.K = d->K; p.R = d->R; p.S = d->S; p.sh = d->stride_h; p.sw = d->stride_w;
+  p.pt = d->pad_h; p.pl = d->pad_w;
+  spc_conv_out_shape(d, &p.Ho, &p.Wo);
+  p.YH = p.Ho; p.YW = p.Wo; p.oy0 = 0; p.ox0 = 0; p.oys = 1; p.oxs = 1;
+  p.w_off = 0; p.wKs = (long long)d->C * d->R * d->S; p.wCs = (long long)d->R * d->S; p.wRs = d->S; p.wSs = 1;
+  return p;
+}
+
+// Launch the direct kernel on the output sub-rectangle [y0,y1) x [x0,x1).
+int fwd_rect(DirectConvParams p, int dtype, int y0, int y1, int x0, int x1, cudaStream_t st) {
+  if (y1 <= y0 || x1 <= x0) return SPC_OK;
+  p.oy0 = y0; p.ox0 = x0;
+  p.pt -= y0 * p.sh; p.pl -= x0 * p.sw;
+  p.Ho = y1 - y0; p.Wo = x1 - x0;
+  return launch_conv_direct(p, dtype, st);
+}
+
+}  // namespace
+}  // namespace spc
+
+using namespace spc;
+
+extern "C" {
+
+void spc_conv_out_shape(const spc_conv_desc* d, int* Ho, int* Wo) {
+  if (Ho) *Ho = (d->H + 2 * d->pad_h - d->R) / d->stride_h + 1;
+  if (Wo) *Wo = (d->W + 2 * d->pad_w - d->S) / d->stride_w + 1;
+}
+
+int spc_conv_uses_tcgen05(const spc_conv_desc* d, int op) {
+  if (!d || d->algo == SPC_ALGO_DIRECT) return 0;
+  return tc_supported(d, op) ? 1 : 0;
+}
+
+size_t spc_conv_workspace_bytes(const spc_conv_desc* d, int op) {
+  if (!d) return 0;
+  return spc_conv_uses_tcgen05(d, op) ? tc_workspace_bytes(d, op) : 0;
+}
+
+int spc_conv2d_fwd(const spc_conv_desc* d, const void* x, const spc_halo* halo, const void* w, const void* bias,
+                   void* y, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  SPC_REQUIRE(x && w && y, "conv_fwd: null tensor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->N == 0) return SPC_OK;
+  DirectConvParams p = fwd_params(d, x, halo, w, bias, y);
+  const bool tc = spc_conv_uses_tcgen05(d, 0);
+  if (d->algo == SPC_ALGO_TCGEN05 && !tc) {
+    set_error("conv_fwd: SPC_ALGO_TCGEN05 requested but the shape is not supported by the tcgen05 path");
+    return SPC_EUNSUPPORTED;
+  }
+  if (!tc) return launch_conv_direct(p, d->dtype, st);
+
+  rc = tc_conv_fwd(d, x, w, bias, y, workspace, workspace_bytes, st);
+  if (rc) return rc;
+  if (!has_halo(halo)) return SPC_OK;
+  // Boundary strips: output rows/cols whose window reaches outside the tile.
+  const int Ho = p.Ho, Wo = p.Wo;
+  const int top = min(Ho, ceil_div(d->pad_h, d->stride_h));
+  int bot0 = ceil_div(d->H + d->pad_h - d->R + 1, d->stride_h);  // first row touching the bottom halo
+  bot0 = max(top, min(Ho, bot0));
+  const int left = min(Wo, ceil_div(d->pad_w, d->stride_w));
+  int right0 = ceil_div(d->W + d->pad_w - d->S + 1, d->stride_w);
+  right0 = max(left, min(Wo, right0));
+  const bool any_top = halo->strip[0] || halo->strip[1] || halo->strip[2];
+  const bool any_bot = halo->strip[6] || halo->strip[7] || halo->strip[8];
+  const bool any_left = halo->strip[0] || halo->strip[3] || halo->strip[6];
+  const bool any_right = halo->strip[2] || halo->strip[5] || halo->strip[8];
+  if (any_top && (rc = fwd_rect(p, d->dtype, 0, top, 0, Wo, st))) return rc;
+  if (any_bot && (rc = fwd_rect(p, d->dtype, bot0, Ho, 0, Wo, st))) return rc;
+  if (any_left && (rc = fwd_rect(p, d->dtype, top, bot0, 0, left, st))) return rc;
+  if (any_right && (rc = fwd_rect(p, d->dtype, top, bot0, right0, Wo, st))) return rc;
+  return SPC_OK;
+}
+
+int spc_conv2d_dgrad(const spc_conv_desc* d, const void* dy, const void* w, void* dx, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  SPC_REQUIRE(dy && w && dx, "conv_dgrad: null tensor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->N == 0) return SPC_OK;
+  const bool tc = spc_conv_uses_tcgen05(d, 1);
+  if (d->algo == SPC_ALGO_TCGEN05 && !tc) {
+    set_error("conv_dgrad: SPC_ALGO_TCGEN05 requested but the shape is not supported by the tcgen05 path");
+    return SPC_EUNSUPPORTED;
+  }
+  if (tc) return tc_conv_dgrad(d, dy, w, dx, workspace, workspace_bytes, st);
+
+  int Ho, Wo;
+  spc_conv_out_shape(d, &Ho, &Wo);
+  const int sh = d->stride_h, sw = d->stride_w, R = d->R, S = d->S;
+  // Decompose by output parity class (a,b): each class is a stride-1 correlation of dy with a
+  // flipped sub-filter (taps r = r_a + sh*t), written with output stride (sh,sw).
+  bool need_zero = false;
+  for (int a = 0; a < sh; ++a) if ((a + d->pad_h) % sh >= R) need_zero = true;
+  for (int b = 0; b < sw; ++b) if ((b + d->pad_w) % sw >= S) need_zero = true;
+  // rows/cols of dx beyond the reach of any output window are also zero; simplest: clear first
+  if (need_zero || (Ho - 1) * sh + R - d->pad_h < d->H || (Wo - 1) * sw + S - d->pad_w < d->W)
+    SPC_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)d->N * d->C * d->H * d->W * dtype_size(d->dtype), st));
+  for (int a = 0; a < sh; ++a) {
+    const int ra = (a + d->pad_h) % sh;
+    if (ra >= R) continue;
+    const int Ta = (R - ra + sh - 1) / sh;
+    const int qa = (a + d->pad_h - ra) / sh;
+    for (int b = 0; b < sw; ++b) {
+      const int sb = (b + d->pad_w) % sw;
+      if (sb >= S) continue;
+      const int Tb = (S - sb + sw - 1) / sw;
+      const int qb = (b + d->pad_w - sb) / sw;
+      DirectConvParams p{};
+      p.in = make_view(dy, nullptr, d->N, d->K, Ho, Wo, 0, 0);
+      p.w = w; p.bias = nullptr; p.y = dx;
+      p.K = d->C; p.R = Ta; p.S = Tb; p.sh = 1; p.sw = 1;
+      p.pt = (Ta - 1) - qa; p.pl = (Tb - 1) - qb;
+      p.Ho = (d->H - a + sh - 1) / sh; p.Wo = (d->W - b + sw - 1) / sw;
+      p.YH = d->H; p.YW = d->W; p.oy0 = a; p.ox0 = b; p.oys = sh; p.oxs = sw;
+      p.w_off = (long long)(ra + sh * (Ta - 1)) * S + (sb + sw * (Tb - 1));
+      p.wKs = (long long)R * S;               // output channel of this launch = c
+      p.wCs = (long long)d->C * R * S;        // input channel of this launch = k
+      p.wRs = -(long long)sh * S; p.wSs = -(long long)sw;
+      rc = launch_conv_direct(p, d->dtype, st);
+      if (rc) return rc;
+    }
+  }
+  return SPC_OK;
+}
+
+int spc_conv2d_wgrad(const spc_conv_desc* d, const void* x, const spc_halo* halo, const void* dy, float* dw,
+                     float* db, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  SPC_REQUIRE(x && dy && dw, "conv_wgrad: null tensor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int Ho, Wo;
+  spc_conv_out_shape(d, &Ho, &Wo);
+  const size_t wn = (size_t)d->K * d->C * d->R * d->S;
+  if (!accumulate) SPC_CHECK_CUDA(cudaMemsetAsync(dw, 0, wn * sizeof(float), st));
+  if (d->N == 0) {
+    if (db && !accumulate) SPC_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * d->K, st));
+    return SPC_OK;
+  }
+  const bool tc = spc_conv_uses_tcgen05(d, 2);
+  if (d->algo == SPC_ALGO_TCGEN05 && !tc) {
+    set_error("conv_wgrad: SPC_ALGO_TCGEN05 requested but the shape is not supported by the tcgen05 path");
+    return SPC_EUNSUPPORTED;
+  }
+  DirectWgradParams p{};
+  p.dy = dy; p.dw = dw;
+  p.K = d->K; p.R = d->R; p.S = d->S; p.sh = d->stride_h; p.sw = d->stride_w; p.ph = d->pad_h; p.pw = d->pad_w;
+  p.Ho = Ho; p.Wo = Wo;
+  if (tc) {
+    rc = tc_conv_wgrad(d, x, dy, dw, /*accumulate=*/1, workspace, workspace_bytes, st);
+    if (rc) return rc;
+    if (has_halo(halo)) {
+      // add the halo pixels' contribution: same kernel over a view that holds ONLY the strips
+      // (interior reads as zero), which is exact by linearity.
+      p.in = make_view(nullptr, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);
+      set_error("conv_wgrad: tcgen05 + halo correction not wired yet");
+      return SPC_EUNSUPPORTED;
+    }
+  } else {
+    p.in = make_view(x, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);
+    rc = launch_wgrad_direct(p, d->dtype, st);
+    if (rc) return rc;
+  }
+  if (db) return launch_bias_grad(dy, db, d->N, d->K, Ho * Wo, d->dtype, accumulate, st);
+  return SPC_OK;
+}
+
+}  // extern "C"

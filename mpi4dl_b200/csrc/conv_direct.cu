@@ -1,0 +1,300 @@
+// conv_direct.cu -- CUDA-core (FFMA) direct convolution kernels for sm_100a.
+//
+// Role in the engine: the shape-complete path.  Every conv_spatial configuration the reference
+// accepts (spatial.py:25-155: any odd RxS, stride 1/2, "same" padding) runs here; the tcgen05
+// GEMM path (gemm_tc.cu) takes over for the shapes that dominate the AmoebaNet-D / ResNet
+// workloads.  It also computes the thin boundary strips whose receptive field touches
+// neighbour halos, reading halo strips in place (TileView) instead of materialising the padded
+// tensor the reference builds with ZeroPad2d + 8 slice copies (spatial.py:1020,405-413).
+#include "common.cuh"
+
+namespace spc {
+
+namespace {
+
+constexpr int DC_TH = 8;        // output rows per CTA (one warp per row)
+constexpr int DC_LANES = 32;    // threads along W
+constexpr int DC_PX = 4;        // output pixels per thread (col = lane + 32*j)
+constexpr int DC_TW = DC_LANES * DC_PX;
+constexpr int DC_KB = 16;       // output channels per CTA
+constexpr int DC_THREADS = DC_TH * DC_LANES;
+
+template <typename T>
+__global__ void __launch_bounds__(DC_THREADS)
+conv_direct_kernel(const DirectConvParams p, const int CB, const int tiles_x, const int kblocks) {
+  extern __shared__ float smem[];
+  const int PH = (DC_TH - 1) * p.sh + p.R;
+  const int PW = (DC_TW - 1) * p.sw + p.S;
+  const int PWp = PW | 1;  // odd pitch
+  float* patch = smem;                          // [CB][PH][PWp]
+  float* wsm = smem + (((size_t)CB * PH * PWp + 3) & ~(size_t)3);  // [CB][R][S][DC_KB], 16B aligned
+
+  const int kb = blockIdx.x % kblocks;
+  const int tile = blockIdx.x / kblocks;
+  const int tx0 = (tile % tiles_x) * DC_TW;
+  const int ty0 = (tile / tiles_x) * DC_TH;
+  const int n = blockIdx.y;
+  const int k0 = kb * DC_KB;
+  const int lane = threadIdx.x % DC_LANES;
+  const int ty = threadIdx.x / DC_LANES;
+  const int C = p.in.C;
+
+  float acc[DC_PX][DC_KB];
+#pragma unroll
+  for (int j = 0; j < DC_PX; ++j)
+#pragma unroll
+    for (int k = 0; k < DC_KB; ++k) acc[j][k] = 0.f;
+
+  const int h_base = ty0 * p.sh - p.pt;
+  const int w_base = tx0 * p.sw - p.pl;
+  const int RS = p.R * p.S;
+
+  for (int c0 = 0; c0 < C; c0 += CB) {
+    __syncthreads();
+    const int patch_elems = CB * PH * PW;
+    for (int i = threadIdx.x; i < patch_elems; i += DC_THREADS) {
+      const int pw = i % PW;
+      const int t = i / PW;
+      const int ph = t % PH;
+      const int c = t / PH;
+      float v = 0.f;
+      if (c0 + c < C) v = tile_load<T>(p.in, n, c0 + c, h_base + ph, w_base + pw);
+      patch[(c * PH + ph) * PWp + pw] = v;
+    }
+    const int w_elems = CB * RS * DC_KB;
+    for (int i = threadIdx.x; i < w_elems; i += DC_THREADS) {
+      const int k = i % DC_KB;
+      const int t = i / DC_KB;
+      const int rs = t % RS;
+      const int c = t / RS;
+      float v = 0.f;
+      if (c0 + c < C && k0 + k < p.K) {
+        const long long idx = p.w_off + (long long)(k0 + k) * p.wKs + (long long)(c0 + c) * p.wCs +
+                              (long long)(rs / p.S) * p.wRs + (long long)(rs % p.S) * p.wSs;
+        v = to_f32<T>(reinterpret_cast<const T*>(p.w)[idx]);
+      }
+      wsm[i] = v;
+    }
+    __syncthreads();
+
+    const int cmax = min(CB, C - c0);
+    for (int c = 0; c < cmax; ++c) {
+      for (int r = 0; r < p.R; ++r) {
+        const float* prow = patch + (c * PH + ty * p.sh + r) * PWp;
+        const float* wrow = wsm + (c * RS + r * p.S) * DC_KB;
+        for (int s = 0; s < p.S; ++s) {
+          float xv[DC_PX];
+#pragma unroll
+          for (int j = 0; j < DC_PX; ++j) xv[j] = prow[(lane + DC_LANES * j) * p.sw + s];
+          const float4* wv = reinterpret_cast<const float4*>(wrow + s * DC_KB);
+          float wk[DC_KB];
+#pragma unroll
+          for (int q = 0; q < DC_KB / 4; ++q) {
+            const float4 t4 = wv[q];
+            wk[4 * q] = t4.x; wk[4 * q + 1] = t4.y; wk[4 * q + 2] = t4.z; wk[4 * q + 3] = t4.w;
+          }
+#pragma unroll
+          for (int j = 0; j < DC_PX; ++j)
+#pragma unroll
+            for (int k = 0; k < DC_KB; ++k) acc[j][k] = fmaf(xv[j], wk[k], acc[j][k]);
+        }
+      }
+    }
+  }
+
+  const int oy = ty0 + ty;
+  if (oy >= p.Ho) return;
+  T* y = reinterpret_cast<T*>(p.y);
+#pragma unroll
+  for (int k = 0; k < DC_KB; ++k) {
+    if (k0 + k >= p.K) break;
+    const float b = p.bias ? to_f32<T>(reinterpret_cast<const T*>(p.bias)[k0 + k]) : 0.f;
+    const size_t row = (((size_t)n * p.K + (k0 + k)) * p.YH + (p.oy0 + oy * p.oys)) * p.YW;
+#pragma unroll
+    for (int j = 0; j < DC_PX; ++j) {
+      const int ox = tx0 + lane + DC_LANES * j;
+      if (ox < p.Wo) y[row + p.ox0 + ox * p.oxs] = from_f32<T>(acc[j][k] + b);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: dw[k][c][r][s] += sum_{n,i,j} dy[n,k,i,j] * in(n,c,i*sh+r-ph, j*sw+s-pw)
+constexpr int WG_KB = 16, WG_CB = 16, WG_TH = 4, WG_TW = 32, WG_THREADS = 256, WG_TAPS = 9;
+
+template <typename T>
+__global__ void __launch_bounds__(WG_THREADS)
+wgrad_direct_kernel(const DirectWgradParams p, const int kblocks, const int cblocks, const int tiles_x,
+                    const int tiles_y, const int tiles_per_cta, const int tap0, const int ntaps) {
+  extern __shared__ float smem[];
+  const int PH = (WG_TH - 1) * p.sh + p.R;
+  const int PW = (WG_TW - 1) * p.sw + p.S;
+  int plane = PH * PW;
+  plane |= 1;
+  constexpr int DYP = WG_TH * WG_TW + 1;
+  float* dys = smem;                 // [WG_KB][DYP]
+  float* xs = smem + WG_KB * DYP;    // [WG_CB][plane]
+
+  const int kb = blockIdx.y % kblocks;
+  const int cb = blockIdx.y / kblocks;
+  const int k0 = kb * WG_KB, c0 = cb * WG_CB;
+  const int kl = threadIdx.x / WG_CB, cl = threadIdx.x % WG_CB;
+  const int C = p.in.C;
+  const int total_tiles = p.in.N * tiles_x * tiles_y;
+  const int t_begin = blockIdx.x * tiles_per_cta;
+  const int t_end = min(total_tiles, t_begin + tiles_per_cta);
+
+  float acc[WG_TAPS];
+#pragma unroll
+  for (int t = 0; t < WG_TAPS; ++t) acc[t] = 0.f;
+
+  const T* dy = reinterpret_cast<const T*>(p.dy);
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const int txi = tile % tiles_x;
+    const int tyi = (tile / tiles_x) % tiles_y;
+    const int n = tile / (tiles_x * tiles_y);
+    const int oy0 = tyi * WG_TH, ox0 = txi * WG_TW;
+    __syncthreads();
+    for (int i = threadIdx.x; i < WG_KB * WG_TH * WG_TW; i += WG_THREADS) {
+      const int px = i % WG_TW;
+      const int py = (i / WG_TW) % WG_TH;
+      const int k = i / (WG_TW * WG_TH);
+      float v = 0.f;
+      if (k0 + k < p.K && oy0 + py < p.Ho && ox0 + px < p.Wo)
+        v = to_f32<T>(dy[(((size_t)n * p.K + k0 + k) * p.Ho + oy0 + py) * p.Wo + ox0 + px]);
+      dys[k * DYP + py * WG_TW + px] = v;
+    }
+    for (int i = threadIdx.x; i < WG_CB * PH * PW; i += WG_THREADS) {
+      const int pw = i % PW;
+      const int ph = (i / PW) % PH;
+      const int c = i / (PW * PH);
+      float v = 0.f;
+      if (c0 + c < C) v = tile_load<T>(p.in, n, c0 + c, oy0 * p.sh - p.ph + ph, ox0 * p.sw - p.pw + pw);
+      xs[c * plane + ph * PW + pw] = v;
+    }
+    __syncthreads();
+    const float* dyr = dys + kl * DYP;
+    const float* xr = xs + cl * plane;
+    for (int py = 0; py < WG_TH; ++py) {
+      for (int px = 0; px < WG_TW; ++px) {
+        const float g = dyr[py * WG_TW + px];
+        const float* xb = xr + (py * p.sh) * PW + px * p.sw;
+#pragma unroll
+        for (int t = 0; t < WG_TAPS; ++t) {
+          if (t < ntaps) {
+            const int tap = tap0 + t;
+            acc[t] = fmaf(g, xb[(tap / p.S) * PW + (tap % p.S)], acc[t]);
+          }
+        }
+      }
+    }
+  }
+  if (k0 + kl < p.K && c0 + cl < C) {
+#pragma unroll
+    for (int t = 0; t < WG_TAPS; ++t) {
+      if (t < ntaps) atomicAdd(&p.dw[((size_t)(k0 + kl) * C + (c0 + cl)) * (p.R * p.S) + tap0 + t], acc[t]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void bias_grad_kernel(const T* __restrict__ dy, float* __restrict__ db, int N, int K, int HW,
+                                 int chunks) {
+  const int k = blockIdx.x;
+  const int chunk = blockIdx.y;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const T* base = dy + ((size_t)n * K + k) * HW;
+    const int per = (HW + chunks - 1) / chunks;
+    const int b = chunk * per, e = min(HW, b + per);
+    for (int i = b + threadIdx.x; i < e; i += blockDim.x) s += to_f32<T>(base[i]);
+  }
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(&db[k], s);
+  }
+}
+
+}  // namespace
+
+int launch_conv_direct(const DirectConvParams& p, int dtype, cudaStream_t st) {
+  if (p.Ho <= 0 || p.Wo <= 0 || p.in.N <= 0) return SPC_OK;
+  const int PH = (DC_TH - 1) * p.sh + p.R;
+  const int PW = ((DC_TW - 1) * p.sw + p.S) | 1;
+  int CB = p.in.C < 8 ? p.in.C : 8;
+  auto bytes = [&](int cb) {
+    return ((((size_t)cb * PH * PW + 3) & ~(size_t)3) + (size_t)cb * p.R * p.S * DC_KB) * sizeof(float);
+  };
+  while (CB > 1 && bytes(CB) > 96 * 1024) CB >>= 1;
+  const size_t smem = bytes(CB);
+  SPC_REQUIRE(smem <= 200 * 1024, "conv_direct: filter %dx%d stride %d needs %zu B smem", p.R, p.S, p.sh, smem);
+  const int tiles_x = ceil_div(p.Wo, DC_TW), tiles_y = ceil_div(p.Ho, DC_TH);
+  const int kblocks = ceil_div(p.K, DC_KB);
+  dim3 grid((unsigned)((size_t)tiles_x * tiles_y * kblocks), p.in.N);
+  if (dtype == SPC_BF16) {
+    SPC_CHECK_CUDA(cudaFuncSetAttribute(conv_direct_kernel<__nv_bfloat16>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    conv_direct_kernel<__nv_bfloat16><<<grid, DC_THREADS, smem, st>>>(p, CB, tiles_x, kblocks);
+  } else {
+    SPC_CHECK_CUDA(cudaFuncSetAttribute(conv_direct_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        200 * 1024));
+    conv_direct_kernel<float><<<grid, DC_THREADS, smem, st>>>(p, CB, tiles_x, kblocks);
+  }
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+int launch_wgrad_direct(const DirectWgradParams& p, int dtype, cudaStream_t st) {
+  if (p.Ho <= 0 || p.Wo <= 0 || p.in.N <= 0) return SPC_OK;
+  const int PH = (WG_TH - 1) * p.sh + p.R;
+  const int PW = (WG_TW - 1) * p.sw + p.S;
+  const size_t smem = ((size_t)WG_KB * (WG_TH * WG_TW + 1) + (size_t)WG_CB * ((PH * PW) | 1)) * sizeof(float);
+  SPC_REQUIRE(smem <= 200 * 1024, "wgrad_direct: filter %dx%d needs %zu B smem", p.R, p.S, smem);
+  const int tiles_x = ceil_div(p.Wo, WG_TW), tiles_y = ceil_div(p.Ho, WG_TH);
+  const int kblocks = ceil_div(p.K, WG_KB), cblocks = ceil_div(p.in.C, WG_CB);
+  const int total_tiles = p.in.N * tiles_x * tiles_y;
+  // enough CTAs for ~4 waves of 148 SMs x 2 resident CTAs, but at least 8 tiles each
+  int want = (148 * 8) / (kblocks * cblocks);
+  if (want < 1) want = 1;
+  int tiles_per_cta = ceil_div(total_tiles, want);
+  if (tiles_per_cta < 8) tiles_per_cta = 8;
+  const int ctas_x = ceil_div(total_tiles, tiles_per_cta);
+  dim3 grid(ctas_x, kblocks * cblocks);
+  const int taps = p.R * p.S;
+  for (int tap0 = 0; tap0 < taps; tap0 += WG_TAPS) {
+    const int nt = taps - tap0 < WG_TAPS ? taps - tap0 : WG_TAPS;
+    if (dtype == SPC_BF16) {
+      SPC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_direct_kernel<__nv_bfloat16>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      wgrad_direct_kernel<__nv_bfloat16><<<grid, WG_THREADS, smem, st>>>(p, kblocks, cblocks, tiles_x, tiles_y,
+                                                                         tiles_per_cta, tap0, nt);
+    } else {
+      SPC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_direct_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
+      wgrad_direct_kernel<float><<<grid, WG_THREADS, smem, st>>>(p, kblocks, cblocks, tiles_x, tiles_y,
+                                                                tiles_per_cta, tap0, nt);
+    }
+    SPC_CHECK_CUDA(cudaGetLastError());
+  }
+  return SPC_OK;
+}
+
+int launch_bias_grad(const void* dy, float* db, int N, int K, int HW, int dtype, int accumulate, cudaStream_t st) {
+  if (!accumulate) SPC_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * K, st));
+  int chunks = ceil_div(HW, 1 << 16);
+  if (chunks > 64) chunks = 64;
+  dim3 grid(K, chunks);
+  if (dtype == SPC_BF16)
+    bias_grad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), db, N, K, HW, chunks);
+  else
+    bias_grad_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(dy), db, N, K, HW, chunks);
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+}  // namespace spc

@@ -1,0 +1,247 @@
+// halo.cu -- halo strip pack / pad / crop kernels and the peer-memory mailbox transport.
+//
+// Replaces the reference's per-direction `.clone()` + torch.cuda.synchronize() + dist.isend /
+// torch.zeros + synchronize + dist.irecv / req.wait() / 8 slice-assign copies
+// (spatial.py:336-413): one pack kernel writes every outgoing strip -- straight into the
+// neighbours' receive buffers when they are CUDA-IPC peer mappings (NVLink P2P stores) -- and
+// a device-side flag (release/acquire at system scope) orders producer and consumer streams.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace spc {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+struct PackParams {
+  const void* x;
+  void* send[9];
+  int N, C, H, W, hh, hw;
+  long long off[10];  // prefix sums of strip element counts
+};
+
+// The strip a tile sends towards direction d is the band of REAL rows/cols adjacent to that
+// edge (reference spatial.py:239-309 locations_send, expressed in unpadded coordinates).
+template <typename T>
+__global__ void halo_pack_kernel(const PackParams p) {
+  const long long total = p.off[9];
+  const T* x = reinterpret_cast<const T*>(p.x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int d = 0;
+#pragma unroll
+    for (int q = 1; q < 9; ++q) d += (i >= p.off[q]) ? 1 : 0;
+    const long long e = i - p.off[d];
+    const int dr = d / 3, dc = d % 3;
+    const int sh = (dr == 1) ? p.H : p.hh;
+    const int sw = (dc == 1) ? p.W : p.hw;
+    const int xw = (int)(e % sw);
+    const int yh = (int)((e / sw) % sh);
+    const long long nc = e / ((long long)sw * sh);
+    const int h = (dr == 0) ? yh : (dr == 2 ? p.H - p.hh + yh : yh);
+    const int w = (dc == 0) ? xw : (dc == 2 ? p.W - p.hw + xw : xw);
+    reinterpret_cast<T*>(p.send[d])[e] = x[(nc * p.H + h) * p.W + w];
+  }
+}
+
+template <typename T>
+__global__ void halo_pad_kernel(const TileView v, T* __restrict__ y) {
+  const int Hp = v.H + 2 * v.hh, Wp = v.W + 2 * v.hw;
+  const size_t total = (size_t)v.N * v.C * Hp * Wp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % Wp);
+    const int h = (int)((i / Wp) % Hp);
+    const size_t nc = i / ((size_t)Wp * Hp);
+    y[i] = from_f32<T>(tile_load<T>(v, (int)(nc / v.C), (int)(nc % v.C), h - v.hh, w - v.hw));
+  }
+}
+
+template <typename T>
+__global__ void halo_crop_kernel(const T* __restrict__ dy, T* __restrict__ dx, int NC, int H, int W, int hh, int hw) {
+  const int Hp = H + 2 * hh, Wp = W + 2 * hw;
+  const size_t total = (size_t)NC * H * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const int h = (int)((i / W) % H);
+    const size_t nc = i / ((size_t)W * H);
+    dx[i] = dy[(nc * Hp + h + hh) * Wp + w + hw];
+  }
+}
+
+__global__ void mailbox_signal_kernel(uint32_t* flag, uint32_t seq) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+}
+
+__global__ void mailbox_wait_kernel(const uint32_t* flag, uint32_t seq) {
+  uint32_t v;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if ((int32_t)(v - seq) >= 0) break;
+    __nanosleep(64);
+  } while (true);
+}
+
+inline int grid_for(size_t total) {
+  size_t b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace
+}  // namespace spc
+
+struct spc_mailbox {
+  void* base;        // data area followed by flags
+  size_t bytes;      // data bytes (rounded up to 256)
+  int nflags;
+  int owner;         // 1: cudaMalloc'ed here, 0: IPC mapping of a peer allocation
+};
+
+extern "C" {
+
+const char* spc_last_error(void) { return spc::g_err; }
+int spc_version(void) { return SPC_VERSION; }
+
+int spc_device_info(int device, int* sm_count, int* cc) {
+  cudaDeviceProp prop;
+  SPC_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc) *cc = prop.major * 10 + prop.minor;
+  SPC_REQUIRE(prop.major == 10, "libspconv is built for sm_100a only; device %d is sm_%d%d", device, prop.major,
+              prop.minor);
+  return SPC_OK;
+}
+
+int spc_halo_pack(int N, int C, int H, int W, int halo_h, int halo_w, int dtype, const void* x, void* const send[9],
+                  void* stream) {
+  SPC_REQUIRE(x && send, "halo_pack: null pointer");
+  SPC_REQUIRE(halo_h <= H && halo_w <= W, "halo_pack: halo (%d,%d) larger than tile (%d,%d)", halo_h, halo_w, H, W);
+  spc::PackParams p{};
+  p.x = x; p.N = N; p.C = C; p.H = H; p.W = W; p.hh = halo_h; p.hw = halo_w;
+  long long off = 0;
+  for (int d = 0; d < 9; ++d) {
+    p.off[d] = off;
+    p.send[d] = (d == 4) ? nullptr : send[d];
+    if (p.send[d]) {
+      const long long sh = (d / 3 == 1) ? H : halo_h, sw = (d % 3 == 1) ? W : halo_w;
+      off += (long long)N * C * sh * sw;
+    }
+  }
+  p.off[9] = off;
+  if (off == 0) return SPC_OK;
+  if (dtype == SPC_BF16)
+    spc::halo_pack_kernel<__nv_bfloat16><<<spc::grid_for(off), 256, 0, (cudaStream_t)stream>>>(p);
+  else
+    spc::halo_pack_kernel<float><<<spc::grid_for(off), 256, 0, (cudaStream_t)stream>>>(p);
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+int spc_halo_pad(int N, int C, int H, int W, int halo_h, int halo_w, int dtype, const void* x, const spc_halo* halo,
+                 void* y, void* stream) {
+  SPC_REQUIRE(x && y, "halo_pad: null pointer");
+  spc::TileView v = spc::make_view(x, halo, N, C, H, W, halo_h, halo_w);
+  const size_t total = (size_t)N * C * (H + 2 * halo_h) * (W + 2 * halo_w);
+  if (total == 0) return SPC_OK;
+  if (dtype == SPC_BF16)
+    spc::halo_pad_kernel<__nv_bfloat16><<<spc::grid_for(total), 256, 0, (cudaStream_t)stream>>>(v, (__nv_bfloat16*)y);
+  else
+    spc::halo_pad_kernel<float><<<spc::grid_for(total), 256, 0, (cudaStream_t)stream>>>(v, (float*)y);
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+int spc_halo_crop(int N, int C, int H, int W, int halo_h, int halo_w, int dtype, const void* dy, void* dx,
+                  void* stream) {
+  SPC_REQUIRE(dy && dx, "halo_crop: null pointer");
+  const size_t total = (size_t)N * C * H * W;
+  if (total == 0) return SPC_OK;
+  if (dtype == SPC_BF16)
+    spc::halo_crop_kernel<__nv_bfloat16><<<spc::grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, N * C, H, W, halo_h, halo_w);
+  else
+    spc::halo_crop_kernel<float><<<spc::grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)dy, (float*)dx, N * C, H, W, halo_h, halo_w);
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+// ---- mailbox ---------------------------------------------------------------------------------
+static size_t mb_round(size_t b) { return (b + 255) & ~(size_t)255; }
+
+int spc_mailbox_create(spc_mailbox** out, size_t bytes, int nflags) {
+  SPC_REQUIRE(out && nflags >= 0, "mailbox_create: bad arguments");
+  spc_mailbox* mb = new spc_mailbox();
+  mb->bytes = mb_round(bytes); mb->nflags = nflags; mb->owner = 1; mb->base = nullptr;
+  const size_t total = mb->bytes + mb_round(sizeof(uint32_t) * (size_t)nflags) + 256;
+  cudaError_t e = cudaMalloc(&mb->base, total);  // plain cudaMalloc: IPC-exportable
+  if (e != cudaSuccess) {
+    spc::set_error("mailbox_create: cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(e));
+    delete mb;
+    return SPC_ENOMEM;
+  }
+  e = cudaMemset(mb->base, 0, total);
+  if (e != cudaSuccess) { spc::set_error("mailbox_create: memset: %s", cudaGetErrorString(e)); return SPC_ECUDA; }
+  *out = mb;
+  return SPC_OK;
+}
+
+void spc_mailbox_destroy(spc_mailbox* mb) {
+  if (!mb) return;
+  if (mb->owner) cudaFree(mb->base); else cudaIpcCloseMemHandle(mb->base);
+  delete mb;
+}
+
+void* spc_mailbox_data(spc_mailbox* mb) { return mb ? mb->base : nullptr; }
+
+int spc_mailbox_export(spc_mailbox* mb, unsigned char handle[SPC_IPC_HANDLE_BYTES]) {
+  SPC_REQUIRE(mb && mb->owner && handle, "mailbox_export: need a locally created mailbox");
+  static_assert(sizeof(cudaIpcMemHandle_t) == SPC_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  SPC_CHECK_CUDA(cudaIpcGetMemHandle(&h, mb->base));
+  memcpy(handle, &h, sizeof(h));
+  return SPC_OK;
+}
+
+int spc_mailbox_open(spc_mailbox** out, const unsigned char handle[SPC_IPC_HANDLE_BYTES], size_t bytes, int nflags) {
+  SPC_REQUIRE(out && handle, "mailbox_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  SPC_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  spc_mailbox* mb = new spc_mailbox();
+  mb->base = p; mb->bytes = mb_round(bytes); mb->nflags = nflags; mb->owner = 0;
+  *out = mb;
+  return SPC_OK;
+}
+
+static uint32_t* mb_flag(spc_mailbox* mb, int idx) {
+  return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(mb->base) + mb->bytes) + idx;
+}
+
+int spc_mailbox_signal(spc_mailbox* peer_mb, int idx, uint32_t seq, void* stream) {
+  SPC_REQUIRE(peer_mb && idx >= 0 && idx < peer_mb->nflags, "mailbox_signal: bad flag index %d", idx);
+  spc::mailbox_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(mb_flag(peer_mb, idx), seq);
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+int spc_mailbox_wait(spc_mailbox* mb, int idx, uint32_t seq, void* stream) {
+  SPC_REQUIRE(mb && idx >= 0 && idx < mb->nflags, "mailbox_wait: bad flag index %d", idx);
+  spc::mailbox_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(mb_flag(mb, idx), seq);
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+// pool.cu -- spatially-partitioned Max/Avg pooling forward and backward for sm_100a.
+//
+// Replaces Pool.forward (reference spatial.py:1503-1509): halo_exchange_layer (pad + 8-way
+// exchange + 8 unpack copies) followed by nn.{Max,Avg}Pool2d(padding=0).  Here the window is
+// read straight from the tile and its halo strips (TileView); the padded tensor never exists.
+// These ops are pure HBM streaming (AI ~ 0): one read of x, one write of y.
+#include "common.cuh"
+
+namespace spc {
+namespace {
+
+struct PoolParams {
+  TileView in;
+  const void* dy;
+  void* out;   // y (fwd) or dx (bwd)
+  int k, stride, pad, mode, Ho, Wo;
+};
+
+// ---- forward, generic: one thread per output element ---------------------------------------
+template <typename T>
+__global__ void pool_fwd_kernel(const PoolParams p) {
+  const size_t total = (size_t)p.in.N * p.in.C * p.Ho * p.Wo;
+  const float inv = 1.f / (float)(p.k * p.k);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % p.Wo);
+    const int oy = (int)((i / p.Wo) % p.Ho);
+    const size_t nc = i / ((size_t)p.Wo * p.Ho);
+    const int c = (int)(nc % p.in.C), n = (int)(nc / p.in.C);
+    const int h0 = oy * p.stride - p.pad, w0 = ox * p.stride - p.pad;
+    float r = (p.mode == SPC_POOL_MAX) ? -INFINITY : 0.f;
+    for (int a = 0; a < p.k; ++a)
+      for (int b = 0; b < p.k; ++b) {
+        const float v = tile_load<T>(p.in, n, c, h0 + a, w0 + b);
+        r = (p.mode == SPC_POOL_MAX) ? fmaxf(r, v) : r + v;
+      }
+    if (p.mode == SPC_POOL_AVG) r *= inv;
+    reinterpret_cast<T*>(p.out)[i] = from_f32<T>(r);
+  }
+}
+
+// ---- forward, vectorised interior path -----------------------------------------------------
+// Each thread produces VEC consecutive outputs of one row.  Input rows are fetched as 16-byte
+// vectors (plus the window overhang as scalars through tile_load), so a warp reads full 128 B
+// lines.  Used when W (and Wo) are multiples of the vector width; edges fall back per element.
+template <typename T, int VEC, int K, int STRIDE>
+__global__ void __launch_bounds__(256)
+pool_fwd_vec_kernel(const PoolParams p) {
+  constexpr int PAD = (K - 1) / 2;
+  constexpr int SPAN = (VEC - 1) * STRIDE + K;           // input columns needed
+  constexpr int IN_VEC = VEC * STRIDE;                    // aligned body columns
+  const int wv = p.Wo / VEC;
+  const size_t total = (size_t)p.in.N * p.in.C * p.Ho * wv;
+  const float inv = 1.f / (float)(K * K);
+  const T* x = reinterpret_cast<const T*>(p.in.x);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int vx = (int)(i % wv);
+    const int oy = (int)((i / wv) % p.Ho);
+    const size_t nc = i / ((size_t)wv * p.Ho);
+    const int c = (int)(nc % p.in.C), n = (int)(nc / p.in.C);
+    const int ox0 = vx * VEC;
+    const int w0 = ox0 * STRIDE - PAD;   // first input column of the span
+    const int h0 = oy * STRIDE - PAD;
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = (p.mode == SPC_POOL_MAX) ? -INFINITY : 0.f;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+      const int h = h0 + a;
+      float row[SPAN];
+      const bool row_in = (unsigned)h < (unsigned)p.in.H;
+      if (row_in) {
+        // body: columns [w0+PAD, w0+PAD+IN_VEC) are aligned to IN_VEC elements
+        const T* src = x + (((size_t)n * p.in.C + c) * p.in.H + h) * p.in.W + (w0 + PAD);
+        if constexpr (sizeof(T) * IN_VEC % 16 == 0) {
+          constexpr int NV = sizeof(T) * IN_VEC / 16;
+          uint4 raw[NV];
+#pragma unroll
+          for (int q = 0; q < NV; ++q) raw[q] = __ldg(reinterpret_cast<const uint4*>(src) + q);
+          const T* e = reinterpret_cast<const T*>(raw);
+#pragma unroll
+          for (int q = 0; q < IN_VEC; ++q)
+            if (PAD + q < SPAN) row[PAD + q] = to_f32<T>(e[q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < IN_VEC; ++q)
+            if (PAD + q < SPAN) row[PAD + q] = to_f32<T>(src[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < PAD; ++q) row[q] = tile_load<T>(p.in, n, c, h, w0 + q);
+#pragma unroll
+        for (int q = PAD + IN_VEC; q < SPAN; ++q) row[q] = tile_load<T>(p.in, n, c, h, w0 + q);
+      } else {
+#pragma unroll
+        for (int q = 0; q < SPAN; ++q) row[q] = tile_load<T>(p.in, n, c, h, w0 + q);
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+          const float v = row[j * STRIDE + b];
+          acc[j] = (p.mode == SPC_POOL_MAX) ? fmaxf(acc[j], v) : acc[j] + v;
+        }
+    }
+    T outv[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) outv[j] = from_f32<T>((p.mode == SPC_POOL_AVG) ? acc[j] * inv : acc[j]);
+    T* dst = reinterpret_cast<T*>(p.out) + (((size_t)n * p.in.C + c) * p.Ho + oy) * p.Wo + ox0;
+    if constexpr (sizeof(T) * VEC == 16) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(outv);
+    } else if constexpr (sizeof(T) * VEC == 8) {
+      *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(outv);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) dst[j] = outv[j];
+    }
+  }
+}
+
+// ---- backward: one thread per dx element (gather over the windows that cover it) -------------
+template <typename T>
+__global__ void pool_bwd_kernel(const PoolParams p) {
+  const int H = p.in.H, W = p.in.W;
+  const size_t total = (size_t)p.in.N * p.in.C * H * W;
+  const float inv = 1.f / (float)(p.k * p.k);
+  const T* dy = reinterpret_cast<const T*>(p.dy);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const int h = (int)((i / W) % H);
+    const size_t nc = i / ((size_t)W * H);
+    const int c = (int)(nc % p.in.C), n = (int)(nc / p.in.C);
+    // windows (oy,ox) with oy*stride - pad <= h <= oy*stride - pad + k - 1
+    const int hp = h + p.pad, wp = w + p.pad;
+    int oy_lo = (hp - p.k + 1 + p.stride - 1);
+    oy_lo = oy_lo < 0 ? 0 : oy_lo / p.stride;
+    int ox_lo = (wp - p.k + 1 + p.stride - 1);
+    ox_lo = ox_lo < 0 ? 0 : ox_lo / p.stride;
+    const int oy_hi = min(p.Ho - 1, hp / p.stride), ox_hi = min(p.Wo - 1, wp / p.stride);
+    float g = 0.f;
+    const T* dyp = dy + nc * (size_t)p.Ho * p.Wo;
+    if (p.mode == SPC_POOL_AVG) {
+      for (int oy = oy_lo; oy <= oy_hi; ++oy)
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) g += to_f32<T>(dyp[(size_t)oy * p.Wo + ox]);
+      g *= inv;
+    } else {
+      for (int oy = oy_lo; oy <= oy_hi; ++oy)
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+          // argmax of window (first maximum in row-major order, ATen max_pool2d semantics)
+          const int h0 = oy * p.stride - p.pad, w0 = ox * p.stride - p.pad;
+          float best = -INFINITY;
+          int bi = 0;
+          for (int a = 0; a < p.k; ++a)
+            for (int b = 0; b < p.k; ++b) {
+              const float v = tile_load<T>(p.in, n, c, h0 + a, w0 + b);
+              if (v > best) { best = v; bi = a * p.k + b; }
+            }
+          if (bi == (h - h0) * p.k + (w - w0)) g += to_f32<T>(dyp[(size_t)oy * p.Wo + ox]);
+        }
+    }
+    reinterpret_cast<T*>(p.out)[i] = from_f32<T>(g);
+  }
+}
+
+template <typename T>
+int run_fwd(const PoolParams& p, cudaStream_t st) {
+  const size_t total = (size_t)p.in.N * p.in.C * p.Ho * p.Wo;
+  if (total == 0) return SPC_OK;
+  constexpr int VEC = 16 / sizeof(T);   // 8 bf16 or 4 fp32 outputs per thread
+  const bool aligned = ((uintptr_t)p.in.x % 16 == 0) && ((uintptr_t)p.out % 16 == 0);
+  const bool vec_ok = aligned && p.Wo % VEC == 0 && p.in.W % (VEC * p.stride) == 0 &&
+                      p.in.W == p.Wo * p.stride;
+  const size_t vtotal = total / VEC;
+  const int blocks = (int)((vtotal + 255) / 256 > 148 * 32 ? 148 * 32 : (vtotal + 255) / 256);
+  if (vec_ok && p.k == 3 && p.stride == 1) {
+    pool_fwd_vec_kernel<T, VEC, 3, 1><<<blocks, 256, 0, st>>>(p);
+  } else if (vec_ok && p.k == 3 && p.stride == 2) {
+    pool_fwd_vec_kernel<T, VEC, 3, 2><<<blocks, 256, 0, st>>>(p);
+  } else if (vec_ok && p.k == 2 && p.stride == 2) {
+    pool_fwd_vec_kernel<T, VEC, 2, 2><<<blocks, 256, 0, st>>>(p);
+  } else {
+    const int b2 = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+    pool_fwd_kernel<T><<<b2, 256, 0, st>>>(p);
+  }
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+template <typename T>
+int run_bwd(const PoolParams& p, cudaStream_t st) {
+  const size_t total = (size_t)p.in.N * p.in.C * p.in.H * p.in.W;
+  if (total == 0) return SPC_OK;
+  const int blocks = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
+  pool_bwd_kernel<T><<<blocks, 256, 0, st>>>(p);
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+int fill(PoolParams& p, const spc_pool_desc* d, const void* x, const spc_halo* halo) {
+  SPC_REQUIRE(d && x, "pool: null descriptor or input");
+  SPC_REQUIRE(d->k >= 1 && d->stride >= 1 && d->pad == (d->k - 1) / 2,
+              "pool: pad must equal floor((k-1)/2) (reference spatial.py:1457-1464), got k=%d pad=%d", d->k, d->pad);
+  SPC_REQUIRE(d->mode == SPC_POOL_MAX || d->mode == SPC_POOL_AVG, "pool: bad mode %d", d->mode);
+  SPC_REQUIRE(d->dtype == SPC_F32 || d->dtype == SPC_BF16, "pool: bad dtype %d", d->dtype);
+  p.in = make_view(x, halo, d->N, d->C, d->H, d->W, d->pad, d->pad);
+  p.k = d->k; p.stride = d->stride; p.pad = d->pad; p.mode = d->mode;
+  p.Ho = (d->H + 2 * d->pad - d->k) / d->stride + 1;
+  p.Wo = (d->W + 2 * d->pad - d->k) / d->stride + 1;
+  return SPC_OK;
+}
+
+}  // namespace
+}  // namespace spc
+
+extern "C" int spc_pool2d_fwd(const spc_pool_desc* d, const void* x, const spc_halo* halo, void* y, void* stream) {
+  spc::PoolParams p{};
+  int rc = spc::fill(p, d, x, halo);
+  if (rc) return rc;
+  p.out = y; p.dy = nullptr;
+  return d->dtype == SPC_BF16 ? spc::run_fwd<__nv_bfloat16>(p, (cudaStream_t)stream)
+                              : spc::run_fwd<float>(p, (cudaStream_t)stream);
+}
+
+extern "C" int spc_pool2d_bwd(const spc_pool_desc* d, const void* x, const spc_halo* halo, const void* dy,
+                              void* dx, void* stream) {
+  spc::PoolParams p{};
+  int rc = spc::fill(p, d, x, halo);
+  if (rc) return rc;
+  p.out = dx; p.dy = dy;
+  return d->dtype == SPC_BF16 ? spc::run_bwd<__nv_bfloat16>(p, (cudaStream_t)stream)
+                              : spc::run_bwd<float>(p, (cudaStream_t)stream);
+}

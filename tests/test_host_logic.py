@@ -1,0 +1,76 @@
+"""CPU-only: host-side mirror of torchgems.spatial -- topology, constructor contracts, and the
+"no CPU fallback" rule."""
+import pytest
+import torch
+
+from mpi4dl_b200.torchgems import spatial
+from oracle import spatial_oracle as so
+
+GRIDS = [("square", 4), ("square", 9), ("square", 16), ("vertical", 2), ("vertical", 4), ("vertical", 8),
+         ("horizontal", 2), ("horizontal", 4), ("horizontal", 8)]
+
+
+@pytest.mark.parametrize("method,P", GRIDS)
+@pytest.mark.parametrize("k", [(3, 3), (1, 7), (7, 1), (5, 5)])
+def test_conv_neighbours_match_oracle(method, P, k):
+    for rank in range(P):
+        m = spatial.conv_spatial(rank, 1, P, 2, 2, k, padding=((k[0] - 1) // 2, (k[1] - 1) // 2), slice_method=method)
+        mask = so.neighbour_mask(method, P, rank, k[0], k[1])
+        assert m.neighbours == mask
+        assert m.rank_neighbours == so.neighbour_ranks(method, P, rank, mask)
+
+
+@pytest.mark.parametrize("method,P", GRIDS)
+def test_halo_layer_and_pool_neighbours(method, P):
+    for rank in range(P):
+        h = spatial.halo_exchange_layer(rank, 1, P, 2, slice_method=method)
+        mask = so.neighbour_mask(method, P, rank)
+        assert h.neighbours == mask and h.rank_neighbours == so.neighbour_ranks(method, P, rank, mask)
+        p = spatial.Pool(rank, 1, P, 3, 1, 1, slice_method=method, operation="AvgPool2d")
+        assert p.neighbours == mask
+        p2 = spatial.Pool(rank, 1, P, 2, 2, 0, slice_method=method, operation="MaxPool2d")
+        assert p2.neighbours is None and p2.halo_len == 0
+
+
+def test_list_num_spatial_parts():
+    m = spatial.conv_spatial(5, 2, [4, 2], 2, 2, 3, padding=1, slice_method="vertical")
+    assert (m.spatial_local_rank, m.num_spatial_parts) == (1, 2)
+    assert m.neighbours == [0, 0, 0, 1, 0, 0, 0, 0, 0]
+    assert m.rank_neighbours[3] == 4
+
+
+def test_conv_spatial_is_a_conv2d_with_reference_state_dict():
+    m = spatial.conv_spatial(0, 1, 4, 3, 8, 3, stride=2, padding=1, bias=True)
+    assert isinstance(m, torch.nn.Conv2d)
+    assert list(m.state_dict().keys()) == ["weight", "bias"]
+    assert m.weight.shape == (8, 3, 3, 3) and m.padding == (0, 0) and m.stride == (2, 2)
+    assert (m.halo_len_height, m.halo_len_width) == (1, 1)
+    ref = torch.nn.Conv2d(3, 8, 3, stride=2)
+    ref.load_state_dict(m.state_dict())
+
+
+def test_reference_assertions():
+    with pytest.raises(AssertionError, match="Spatial not supported yet"):
+        spatial.conv_spatial(0, 1, 4, 3, 8, 3, padding=0)
+    with pytest.raises(AssertionError, match="halo_len should be equal to padding"):
+        spatial.Pool(0, 1, 4, 3, 1, 0, operation="AvgPool2d")
+    with pytest.raises(AssertionError, match="operation is none"):
+        spatial.Pool(0, 1, 4, 3, 1, 1)
+    with pytest.raises(AssertionError, match="Only MaxPool2d and AvgPool2d"):
+        spatial.Pool(0, 1, 4, 3, 1, 1, operation="LPPool2d")
+    with pytest.raises(AssertionError, match="Custom Halo Len"):
+        spatial.conv_spatial(0, 1, 4, 3, 8, 3, padding=1, halo_len=1)
+
+
+def test_no_cpu_fallback():
+    m = spatial.conv_spatial(0, 1, 1, 3, 4, 3, padding=1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        spatial.Pool(0, 1, 1, 3, 1, 1, operation="AvgPool2d")(torch.zeros(1, 3, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        spatial.halo_exchange_layer(0, 1, 1, 1)(torch.zeros(1, 3, 8, 8))
+
+
+def test_north_star_aliases():
+    assert spatial.pool_spatial is spatial.Pool and spatial.halo_exchange is spatial.halo_exchange_layer
