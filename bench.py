@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py -- hot-path throughput of the spatial-parallel conv engine on B200.
+
+One "step" = one pass of the hot path over one synthetic image: forward and backward (dgrad +
+wgrad) of every conv / pool layer of the reference's SPATIAL STAGE of AmoebaNet-D(18,416) at
+8192x8192 (split_size=4: stem1-3 + cell1_normal1-3 = 62 convs + 13 pools; shapes extracted
+from the reference's own model, tests/golden/layers_amoebanetd_sp4.json), each GPU working on
+its tile (halo exchange between tiles + weight-grad allreduce at N>1), through the public
+torchgems.spatial modules (which call libspconv.so through the C ABI).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference ...                     # the reference's CPU path (port)
+
+Prints ONE JSON line (see the task contract): metric/value/unit, ms_per_step, e2e, roofline,
+cpu_baseline, clocks, gpu_launches.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "amoebanet": ("layers_amoebanetd_sp4.json", "AmoebaNet-D(18,416) spatial stage (split_size=4) @ 8192x8192"),
+    "resnet": ("layers_resnet101_sp2.json", "ResNet-v2-101 spatial stage (split_size=2) @ 4096x4096"),
+}
+METRIC = "images/sec (device-timed, max over ranks) AmoebaNet-D 8192^2 hot path (spatial-stage conv/pool fwd+bwd)"
+
+
+def load_layers(name):
+    fn, desc = WORKLOADS[name]
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", fn)))
+    return d, desc
+
+
+def grid_for(n):
+    """Tiling used for N GPUs: square when N is a perfect square, else vertical strips
+    (reference train_spatial.py:241-290; square needs sqrt(P) integer)."""
+    if n == 1:
+        return "square", 1, 1
+    q = int(round(n ** 0.5))
+    if q * q == n:
+        return "square", q, q
+    return "vertical", 1, n
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, l in self.lines:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except Exception:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def conv_bytes_flops(l, tile_h, tile_w, esz):
+    Ho = (tile_h + 2 * l["pad_h"] - l["R"]) // l["stride_h"] + 1
+    Wo = (tile_w + 2 * l["pad_w"] - l["S"]) // l["stride_w"] + 1
+    xin = l["C"] * tile_h * tile_w
+    yout = l["K"] * Ho * Wo
+    wn = l["K"] * l["C"] * l["R"] * l["S"]
+    fl = 2.0 * wn * Ho * Wo
+    return dict(fwd=((xin + yout + wn) * esz, fl), dgrad=((xin + yout + wn) * esz, fl),
+                wgrad=((xin + yout) * esz + wn * 4, fl))
+
+
+def pool_bytes(l, tile_h, tile_w, esz):
+    Ho = (tile_h + 2 * l["pad"] - l["k"]) // l["stride"] + 1
+    Wo = (tile_w + 2 * l["pad"] - l["k"]) // l["stride"] + 1
+    return dict(fwd=((l["C"] * tile_h * tile_w + l["C"] * Ho * Wo) * esz, 0.0),
+                bwd=((l["C"] * tile_h * tile_w * 2 + l["C"] * Ho * Wo) * esz, 0.0))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's own CPU path (restated with the PyTorch CPU ops it calls,
+    oracle/ref_port_torch.py) on a bounded sample of the workload, all host threads."""
+    import torch
+
+    from oracle import ref_port_torch as rp
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d, desc = load_layers(args.workload)
+    scale = args.cpu_scale
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        rp.run_workload(d["layers"], scale)
+    times = [rp.run_workload(d["layers"], scale) for _ in range(max(1, min(args.steps, 5)))]
+    t = statistics.median(times)
+    # the sample is the same layer list at 1/scale linear size: work per image scales with scale^2
+    val = 1.0 / (t * scale * scale)
+    sample = "all %d layers fwd+bwd at %dx%d (1/%d linear size), fp32, torch CPU ops, extrapolated x%d to %d^2" % (
+        len(d["layers"]), d["image"] // scale, d["image"] // scale, scale, scale * scale, d["image"])
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "images/sec", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": 1, "ms_per_step": t * 1e3 * scale * scale, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "impl_note": "reference CPU path restated (pad + F.conv2d/F.*_pool2d + autograd)"},
+        "cpu_baseline": {"value": val, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="amoebanet", choices=list(WORKLOADS))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--image", type=int, default=0, help="override the full image edge (debug)")
+    ap.add_argument("--cpu-scale", type=int, default=16, help="linear down-scale of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--algo", default="auto", choices=["auto", "direct"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from mpi4dl_b200 import _lib
+    from mpi4dl_b200.torchgems import spatial
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    import ctypes as C
+    sm, cc = C.c_int(), C.c_int()
+    _lib.check(L.spc_device_info(local_rank, C.byref(sm), C.byref(cc)), "spc_device_info")
+
+    d, desc = load_layers(args.workload)
+    image = args.image or d["image"]
+    shrink = d["image"] // image
+    method, gr, gc = grid_for(world)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    esz = 2 if dtype == torch.bfloat16 else 4
+    algo = _lib.SPC_ALGO_DIRECT if args.algo == "direct" else _lib.SPC_ALGO_AUTO
+
+    # ---- build one module per distinct layer shape (weights shared by repeats) ------------------
+    uniq = {}
+    order = []
+    for l in d["layers"]:
+        l = dict(l)
+        l["H"] //= shrink
+        l["W"] //= shrink
+        th, tw = l["H"] // gr, l["W"] // gc
+        key = json.dumps({k: v for k, v in l.items() if k != "kind"}, sort_keys=True)
+        if key not in uniq:
+            if l["op"] == "conv":
+                m = spatial.conv_spatial(rank, 1, world, l["C"], l["K"], (l["R"], l["S"]),
+                                         stride=(l["stride_h"], l["stride_w"]), padding=(l["pad_h"], l["pad_w"]),
+                                         bias=False, slice_method=method).to(dev).to(dtype)
+                m.algo = algo
+            else:
+                m = spatial.Pool(rank, 1, world, l["k"], l["stride"], l["pad"], slice_method=method,
+                                 operation="MaxPool2d" if l["mode"] == "max" else "AvgPool2d")
+            uniq[key] = dict(layer=l, mod=m, th=th, tw=tw, count=0, first=(len(order) == 0))
+        uniq[key]["count"] += 1
+        order.append(key)
+
+    # ---- scratch tensors (inputs larger than L2; reused across layers) --------------------------
+    max_in = max(u["layer"]["C"] * u["th"] * u["tw"] for u in uniq.values())
+    max_out = 0
+    for u in uniq.values():
+        l = u["layer"]
+        if l["op"] == "conv":
+            ho = (u["th"] + 2 * l["pad_h"] - l["R"]) // l["stride_h"] + 1
+            wo = (u["tw"] + 2 * l["pad_w"] - l["S"]) // l["stride_w"] + 1
+            u["out_shape"] = (1, l["K"], ho, wo)
+        else:
+            ho = (u["th"] + 2 * l["pad"] - l["k"]) // l["stride"] + 1
+            wo = (u["tw"] + 2 * l["pad"] - l["k"]) // l["stride"] + 1
+            u["out_shape"] = (1, l["C"], ho, wo)
+        u["in_shape"] = (1, l["C"], u["th"], u["tw"])
+        max_out = max(max_out, u["out_shape"][1] * ho * wo)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    scratch_x = torch.empty(max_in, dtype=dtype, device=dev).normal_(generator=g)
+    scratch_gy = (torch.empty(max_out, dtype=dtype, device=dev).normal_(generator=g) * 0.01)
+    total_params = sum(u["count"] * (u["mod"].weight.numel() if u["layer"]["op"] == "conv" else 0) for u in uniq.values())
+    flat_grads = torch.zeros(total_params, dtype=dtype, device=dev)
+    # host image tile for the e2e arm (the stem conv's input), pinned
+    first = uniq[order[0]]
+    host_img = torch.randn(first["in_shape"], dtype=dtype).pin_memory()
+    dev_img = torch.empty(first["in_shape"], dtype=dtype, device=dev)
+    host_out = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def view(buf, shape):
+        n = 1
+        for s in shape:
+            n *= s
+        return buf[:n].view(shape)
+
+    def step(e2e=False):
+        off = 0
+        last = None
+        if e2e:
+            dev_img.copy_(host_img, non_blocking=True)
+        for i, key in enumerate(order):
+            u = uniq[key]
+            x = dev_img if (e2e and i == 0) else view(scratch_x, u["in_shape"])
+            x = x.detach()
+            if not u["first"]:
+                x.requires_grad_(True)
+            y = u["mod"](x)
+            y.backward(view(scratch_gy, u["out_shape"]))
+            x.grad = None
+            if u["layer"]["op"] == "conv":
+                w = u["mod"].weight
+                flat_grads[off:off + w.numel()].copy_(w.grad.view(-1))   # SyncAllreduce flatten (comm.py:414-438)
+                off += w.numel()
+                w.grad = None
+            last = y
+        if world > 1:
+            dist.all_reduce(flat_grads)                                   # comm.py:506-514
+            flat_grads.div_(world)
+        if e2e:
+            host_out.copy_(last.detach().float().sum().view(1), non_blocking=True)
+        return last
+
+    def timed(nsteps, e2e):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nsteps):
+            step(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_wall0 = time.time()
+    L.spc_launch_count(1)
+    ms_total = timed(args.steps, False)
+    launches = int(L.spc_launch_count(0))
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    step(True)
+    ms_e2e = timed(args.steps, True)
+
+    # ---- per-kernel timing pass (CUDA events around single ops) -> roofline ----------------------
+    kinds = {}
+
+    def ev_time(fn, reps=1):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    per_layer = []
+    for key, u in uniq.items():
+        l = u["layer"]
+        x = view(scratch_x, u["in_shape"]).detach().requires_grad_(not u["first"])
+        gy = view(scratch_gy, u["out_shape"])
+        yy = [None]
+
+        def f_fwd():
+            yy[0] = u["mod"](x)
+
+        t_f = ev_time(f_fwd)
+
+        def f_bwd():
+            yy[0].backward(gy, retain_graph=True)
+            x.grad = None
+
+        t_b = ev_time(f_bwd)
+        if l["op"] == "conv":
+            bf = conv_bytes_flops(l, u["th"], u["tw"], esz)
+            dsc = _lib.ConvDesc(1, l["C"], u["th"], u["tw"], l["K"], l["R"], l["S"], l["stride_h"], l["stride_w"],
+                                l["pad_h"], l["pad_w"], _lib.dtype_code(dtype), algo)
+            tc = [L.spc_conv_uses_tcgen05(C.byref(dsc), op) for op in range(3)]
+            kname = "conv_fwd_" + ("tcgen05" if tc[0] else "direct")
+            byts, fl = bf["fwd"]
+            nb = 1 if u["first"] else 2
+            bb = bf["wgrad"][0] + (0 if u["first"] else bf["dgrad"][0])
+            fb = bf["wgrad"][1] + (0 if u["first"] else bf["dgrad"][1])
+            kb = "conv_bwd_" + ("tcgen05" if tc[2] else "direct")
+            u["mod"].weight.grad = None
+        else:
+            pb = pool_bytes(l, u["th"], u["tw"], esz)
+            kname, (byts, fl) = "pool_fwd", pb["fwd"]
+            kb, (bb, fb) = "pool_bwd", pb["bwd"]
+        for kn, tt, by, f in ((kname, t_f, byts, fl), (kb, t_b, bb, fb)):
+            k = kinds.setdefault(kn, dict(ms=0.0, bytes=0.0, flops=0.0, launches=0))
+            k["ms"] += tt * u["count"]
+            k["bytes"] += by * u["count"]
+            k["flops"] += f * u["count"]
+            k["launches"] += u["count"]
+        per_layer.append(dict(layer={k: v for k, v in l.items() if k in ("op", "C", "K", "R", "S", "stride_h", "k", "stride", "mode", "H", "W")},
+                              count=u["count"], fwd_ms=round(t_f, 3), bwd_ms=round(t_b, 3)))
+        del yy
+
+    hbm, tfs, peak_src = peaks()
+    dom = max(kinds.items(), key=lambda kv: kv[1]["ms"])
+    dk = dom[1]
+    t_hbm = dk["bytes"] / (hbm * 1e9)
+    t_tc = dk["flops"] / (tfs * 1e12)
+    if t_hbm >= t_tc:
+        roof = {"bound": "hbm", "achieved": dk["bytes"] / (dk["ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s"}
+    else:
+        roof = {"bound": "tensor", "achieved": dk["flops"] / (dk["ms"] * 1e-3) / 1e12, "peak": tfs, "unit": "TFLOP/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["traffic"] = None
+    roof["kernel"] = dom[0]
+    roof["peak_source"] = peak_src
+    roof["share_of_step"] = dk["ms"] / sum(k["ms"] for k in kinds.values())
+    # whole-step roofline (BASELINE.md definition: sum_layers max(F/P, B/BW) / n_gpus)
+    t_roof = sum(max(k["bytes"] / (hbm * 1e9), k["flops"] / (tfs * 1e12)) for k in kinds.values())
+    roof["step_roofline_ms"] = t_roof * 1e3
+    roof["step_frac"] = t_roof * 1e3 / (ms_total / args.steps)
+    roof["kinds"] = {k: dict(ms=round(v["ms"], 3), GBps=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                             TFLOPs=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)) for k, v in kinds.items()}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import ref_port_torch as rp
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            scale = args.cpu_scale * shrink
+            rp.run_workload(d["layers"], scale)
+            tcpu = rp.run_workload(d["layers"], scale)
+            cpu = {"value": 1.0 / (tcpu * (scale / shrink) ** 2), "unit": "images/sec", "cores": cores, "kind": "port",
+                   "sample": "all %d layers fwd+bwd at 1/%d linear size in fp32 with the torch CPU ops the reference calls "
+                             "(oracle/ref_port_torch.py), %.1f s, extrapolated by area" % (len(d["layers"]), scale, tcpu)}
+        ms_step = ms_total / args.steps
+        out = {
+            "metric": METRIC, "value": 1000.0 / ms_step, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": args.dtype if args.dtype != "fp32" else "f32", "data": "synthetic",
+            "config": {"workload": desc if not args.image else desc + " [debug image %d]" % image,
+                       "global_batch": 1, "parallelism": "sp%d-%s" % (world, method), "tile": [image // gr, image // gc],
+                       "layers": len(order), "l2_policy": "inputs larger than L2 (every layer tensor >> 126 MB)",
+                       "note": "conv_spatial + Pool layers AND the 1x1 nn.Conv2d layers inside the spatial cells, "
+                               "all through torchgems.spatial modules -> libspconv C ABI; BN/ReLU/concat excluded",
+                       "algo": args.algo, "sm_count": sm.value},
+            "e2e": {"value": 1000.0 / (ms_e2e / args.steps), "unit": "images/sec",
+                    "h2d_bytes_per_step": host_img.numel() * host_img.element_size(), "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "per_layer": per_layer,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,8 @@ int         spc_version(void);
 const char* spc_last_error(void);
 /* sm count, compute capability major*10+minor; fails loudly when no sm_100 device is present */
 int         spc_device_info(int device, int* sm_count, int* cc);
+/* number of kernels this library has launched since the last reset (bench.py's gpu_launches) */
+long long   spc_launch_count(int reset);
 
 /* ---- convolution ------------------------------------------------------------------------ */
 /* y = conv(pad+halo(x), w) + bias.   Replaces spatial.py:1019-1029 (ZeroPad2d :1020,

@@ -80,9 +80,9 @@ int spc_conv2d_fwd(const spc_conv_desc* d, const void* x, const spc_halo* halo, 
                    void* y, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
-  SPC_REQUIRE(x && w && y, "conv_fwd: null tensor pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (d->N == 0) return SPC_OK;
+  SPC_REQUIRE(x && w && y, "conv_fwd: null tensor pointer");
   DirectConvParams p = fwd_params(d, x, halo, w, bias, y);
   const bool tc = spc_conv_uses_tcgen05(d, 0);
   if (d->algo == SPC_ALGO_TCGEN05 && !tc) {
@@ -117,9 +117,9 @@ int spc_conv2d_dgrad(const spc_conv_desc* d, const void* dy, const void* w, void
                      size_t workspace_bytes, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
-  SPC_REQUIRE(dy && w && dx, "conv_dgrad: null tensor pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (d->N == 0) return SPC_OK;
+  SPC_REQUIRE(dy && w && dx, "conv_dgrad: null tensor pointer");
   const bool tc = spc_conv_uses_tcgen05(d, 1);
   if (d->algo == SPC_ALGO_TCGEN05 && !tc) {
     set_error("conv_dgrad: SPC_ALGO_TCGEN05 requested but the shape is not supported by the tcgen05 path");
@@ -170,7 +170,7 @@ int spc_conv2d_wgrad(const spc_conv_desc* d, const void* x, const spc_halo* halo
                      float* db, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = validate(d);
   if (rc) return rc;
-  SPC_REQUIRE(x && dy && dw, "conv_wgrad: null tensor pointer");
+  SPC_REQUIRE(dw && (d->N == 0 || (x && dy)), "conv_wgrad: null tensor pointer");
   cudaStream_t st = (cudaStream_t)stream;
   int Ho, Wo;
   spc_conv_out_shape(d, &Ho, &Wo);

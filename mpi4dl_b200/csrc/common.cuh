@@ -10,6 +10,7 @@
 namespace spc {
 
 void set_error(const char* fmt, ...);
+void count_launch(int n = 1);   // bookkeeping for spc_launch_count()
 
 #define SPC_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \

@@ -245,6 +245,7 @@ int launch_conv_direct(const DirectConvParams& p, int dtype, cudaStream_t st) {
                                         200 * 1024));
     conv_direct_kernel<float><<<grid, DC_THREADS, smem, st>>>(p, CB, tiles_x, kblocks);
   }
+  spc::count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
 }
@@ -279,7 +280,8 @@ int launch_wgrad_direct(const DirectWgradParams& p, int dtype, cudaStream_t st) 
       wgrad_direct_kernel<float><<<grid, WG_THREADS, smem, st>>>(p, kblocks, cblocks, tiles_x, tiles_y,
                                                                 tiles_per_cta, tap0, nt);
     }
-    SPC_CHECK_CUDA(cudaGetLastError());
+    spc::count_launch();
+  SPC_CHECK_CUDA(cudaGetLastError());
   }
   return SPC_OK;
 }
@@ -293,6 +295,7 @@ int launch_bias_grad(const void* dy, float* db, int N, int K, int HW, int dtype,
     bias_grad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(dy), db, N, K, HW, chunks);
   else
     bias_grad_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(dy), db, N, K, HW, chunks);
+  spc::count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
 }

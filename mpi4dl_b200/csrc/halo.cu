@@ -20,6 +20,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+long long launches(int reset) { long long v = g_launches; if (reset) g_launches = 0; return v; }
+
 namespace {
 
 struct PackParams {
@@ -112,6 +116,7 @@ extern "C" {
 
 const char* spc_last_error(void) { return spc::g_err; }
 int spc_version(void) { return SPC_VERSION; }
+long long spc_launch_count(int reset) { return spc::launches(reset); }
 
 int spc_device_info(int device, int* sm_count, int* cc) {
   cudaDeviceProp prop;
@@ -144,6 +149,7 @@ int spc_halo_pack(int N, int C, int H, int W, int halo_h, int halo_w, int dtype,
     spc::halo_pack_kernel<__nv_bfloat16><<<spc::grid_for(off), 256, 0, (cudaStream_t)stream>>>(p);
   else
     spc::halo_pack_kernel<float><<<spc::grid_for(off), 256, 0, (cudaStream_t)stream>>>(p);
+  spc::count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
 }
@@ -158,6 +164,7 @@ int spc_halo_pad(int N, int C, int H, int W, int halo_h, int halo_w, int dtype, 
     spc::halo_pad_kernel<__nv_bfloat16><<<spc::grid_for(total), 256, 0, (cudaStream_t)stream>>>(v, (__nv_bfloat16*)y);
   else
     spc::halo_pad_kernel<float><<<spc::grid_for(total), 256, 0, (cudaStream_t)stream>>>(v, (float*)y);
+  spc::count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
 }
@@ -173,6 +180,7 @@ int spc_halo_crop(int N, int C, int H, int W, int halo_h, int halo_w, int dtype,
   else
     spc::halo_crop_kernel<float><<<spc::grid_for(total), 256, 0, (cudaStream_t)stream>>>(
         (const float*)dy, (float*)dx, N * C, H, W, halo_h, halo_w);
+  spc::count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
 }
@@ -233,6 +241,7 @@ static uint32_t* mb_flag(spc_mailbox* mb, int idx) {
 int spc_mailbox_signal(spc_mailbox* peer_mb, int idx, uint32_t seq, void* stream) {
   SPC_REQUIRE(peer_mb && idx >= 0 && idx < peer_mb->nflags, "mailbox_signal: bad flag index %d", idx);
   spc::mailbox_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(mb_flag(peer_mb, idx), seq);
+  spc::count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
 }
@@ -240,6 +249,7 @@ int spc_mailbox_signal(spc_mailbox* peer_mb, int idx, uint32_t seq, void* stream
 int spc_mailbox_wait(spc_mailbox* mb, int idx, uint32_t seq, void* stream) {
   SPC_REQUIRE(mb && idx >= 0 && idx < mb->nflags, "mailbox_wait: bad flag index %d", idx);
   spc::mailbox_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(mb_flag(mb, idx), seq);
+  spc::count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
 }

@@ -180,6 +180,7 @@ int run_fwd(const PoolParams& p, cudaStream_t st) {
     const int b2 = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
     pool_fwd_kernel<T><<<b2, 256, 0, st>>>(p);
   }
+  spc::count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
 }
@@ -190,6 +191,7 @@ int run_bwd(const PoolParams& p, cudaStream_t st) {
   if (total == 0) return SPC_OK;
   const int blocks = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
   pool_bwd_kernel<T><<<blocks, 256, 0, st>>>(p);
+  spc::count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
 }
