@@ -1,9 +1,343 @@
-// gemm_tc.cu -- tcgen05 (5th-gen tensor core) implicit-GEMM path.  [stub: filled in next]
+// gemm_tc.cu -- tcgen05 (5th-gen tensor core) GEMM path for the 1x1 ("pointwise") convolutions
+// that carry ~90% of the HBM traffic of the AmoebaNet-D / ResNet spatial stages.
+//
+// NCHW makes a 1x1 convolution a plain GEMM per image with NO layout change:
+//     fprop : Y[K x P] = W [K x C] * X [C x P]        P = H*W pixels, contiguous in memory
+//     dgrad : dX[C x P] = W^T[C x K] * dY[K x P]
+//     wgrad : dW[K x C] = dY[K x P] * X[C x P]^T       (reduction over pixels)
+// fprop/dgrad: A = (padded) weights, K-major, TMA box {64 ch, 128 rows}, SWIZZLE_128B;
+//              B = activations read IN PLACE by TMA as an MN-major operand: box {64 px, 64 ch}
+//              -> smem [ch][64 px] (128 B rows, SWIZZLE_128B); accumulator D[128 out-ch x BN px]
+//              lives in TMEM.  The epilogue thread that owns TMEM lane k holds BN consecutive
+//              pixels of output channel k, i.e. a contiguous NCHW run -> 16-byte stores.
+// wgrad:       both operands K-major straight from NCHW (pixels = reduction dim, contiguous).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+// warps 2..5 = epilogue (TMEM -> registers -> global).  Persistent CTAs, one per SM.
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace spc {
-bool tc_supported(const spc_conv_desc*, int) { return false; }
-size_t tc_workspace_bytes(const spc_conv_desc*, int) { return 0; }
-int tc_conv_fwd(const spc_conv_desc*, const void*, const void*, const void*, void*, void*, size_t, cudaStream_t) { return SPC_EUNSUPPORTED; }
-int tc_conv_dgrad(const spc_conv_desc*, const void*, const void*, void*, void*, size_t, cudaStream_t) { return SPC_EUNSUPPORTED; }
-int tc_conv_wgrad(const spc_conv_desc*, const void*, const void*, float*, int, void*, size_t, cudaStream_t) { return SPC_EUNSUPPORTED; }
+
+using namespace tc;
+
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int BK = 64;                 // channels per pipeline stage (one 128-byte swizzle row of A)
+constexpr int A_BLK_BYTES = 128 * BK * 2;   // one 128-row M block of A per stage: 16 KB
+constexpr int B_BLK_BYTES = BK * 64 * 2;    // one 64-pixel block of B per stage: 8 KB
+constexpr int TMEM_COLS = 512;
+
+// ---- host: TMA descriptor encode (driver entry point fetched through the runtime) -------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor map, rank <= 4; dims/strides innermost first (strides in BYTES for dims 1..).
+int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return SPC_ECUDA;
+  }
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gs[i - 1] = strides_bytes[i];
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu] strides=[%llu,%llu]", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 1 ? strides_bytes[1] : 0),
+              (unsigned long long)(rank > 2 ? strides_bytes[2] : 0));
+    return SPC_ECUDA;
+  }
+  return SPC_OK;
+}
+
+// ---- weight repack: Wp[m][c] (bf16, zero padded to [Mpad][Cpad]) --------------------------------
+// transpose == 0: Wp[m][c] = w[m*ld + c]       (fprop: m = out channel K, c = in channel C)
+// transpose == 1: Wp[m][c] = w[c*ld + m]       (dgrad: m = C, c = K)
+__global__ void repack_weights_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wp, int M,
+                                      int Cc, int Mpad, int Cpad, int ld, int transpose) {
+  const int total = Mpad * Cpad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % Cpad, m = i / Cpad;
+    __nv_bfloat16 v = __float2bfloat16(0.f);
+    if (m < M && c < Cc) v = transpose ? w[(size_t)c * ld + m] : w[(size_t)m * ld + c];
+    wp[i] = v;
+  }
+}
+
+// ---- fprop / dgrad kernel -----------------------------------------------------------------------
+struct PwParams {
+  __nv_bfloat16* y;            // [N][M][P]
+  const __nv_bfloat16* bias;   // [M] or null
+  int M;                       // valid output channels
+  int Cin;                     // reduction length (input channels)
+  int P;                       // pixels per image
+  int N;                       // images
+  int tiles_per_image;
+  int num_mg;                  // groups of 512 output channels (X tile re-read per group, from L2)
+  int num_tiles;               // N * tiles_per_image * num_mg
+};
+
+template <int MB, int BN, int STAGES, int ACC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+               const PwParams p) {
+  constexpr int NB = BN / 64;                               // 64-pixel blocks of B per stage
+  constexpr int STAGE_BYTES = MB * A_BLK_BYTES + NB * B_BLK_BYTES;
+  static_assert(ACC * MB * BN <= TMEM_COLS, "TMEM budget");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kchunks = (p.Cin + BK - 1) / BK;
+  const int ksteps_total = (p.Cin + 15) / 16;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < ACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_w);
+      tma_prefetch_desc(&tmap_x);
+      int s = 0, ph = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int mg = t % p.num_mg;
+        const int tt = t / p.num_mg;
+        const int n = tt / p.tiles_per_image;
+        const int p0 = (tt % p.tiles_per_image) * BN;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) tma_load_2d(st + mb * A_BLK_BYTES, &tmap_w, &full[s], kc * BK, mg * 512 + mb * 128);
+#pragma unroll
+          for (int j = 0; j < NB; ++j)
+            tma_load_3d(st + MB * A_BLK_BYTES + j * B_BLK_BYTES, &tmap_x, &full[s], p0 + j * 64, kc * BK, n);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t IDESC = umma_idesc_bf16(128, BN, /*a_mn=*/0, /*b_mn=*/1);
+      int s = 0, ph = 0, a = 0, aph = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        mbar_wait(&tempty[a], aph ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + MB * A_BLK_BYTES;
+          const int nsteps = min(4, ksteps_total - kc * 4);
+          for (int ks = 0; ks < nsteps; ++ks) {
+            // B: MN-major SW128. 16 channels = two 8-row groups (SBO = 1024 B); 64-px blocks at LBO = 8 KB
+            const uint64_t bdesc = umma_desc(sb + ks * 2048, B_BLK_BYTES, 1024);
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+              // A: K-major SW128. 8-row groups at SBO = 1024 B; +32 B per 16-channel k-step
+              const uint64_t adesc = umma_desc(sa + mb * A_BLK_BYTES + ks * 32, 16, 1024);
+              umma_bf16(tmem_base + (a * MB + mb) * BN, adesc, bdesc, IDESC, (kc | ks) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[s]);
+          if (kc == kchunks - 1) umma_commit(&tfull[a]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        if (++a == ACC) { a = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ================= epilogue: TMEM -> registers -> global (NCHW rows) =================
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may access
+    int a = 0, aph = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const int mg = t % p.num_mg;
+      const int tt = t / p.num_mg;
+      const int n = tt / p.tiles_per_image;
+      const int p0 = (tt % p.tiles_per_image) * BN;
+      mbar_wait(&tfull[a], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int mb = 0; mb < MB; ++mb) {
+        const int k = mg * 512 + mb * 128 + quarter * 32 + lane;
+        const bool krow = k < p.M;
+        const float bias = (krow && p.bias) ? __bfloat162float(p.bias[k]) : 0.f;
+        __nv_bfloat16* yrow = p.y + ((size_t)n * p.M + (krow ? k : 0)) * p.P;
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (a * MB + mb) * BN + cc * 32, r);
+          tmem_ld_wait();
+          if (krow) {
+            const int px = p0 + cc * 32;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (px + j * 8 + 8 <= p.P) {
+                uint4 v;
+                v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]) + bias, __uint_as_float(r[8 * j + 1]) + bias);
+                v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]) + bias, __uint_as_float(r[8 * j + 3]) + bias);
+                v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]) + bias, __uint_as_float(r[8 * j + 5]) + bias);
+                v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]) + bias, __uint_as_float(r[8 * j + 7]) + bias);
+                *reinterpret_cast<uint4*>(yrow + px + j * 8) = v;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[a]);
+      if (++a == ACC) { a = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int MB, int BN, int STAGES, int ACC>
+int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const PwParams& p, cudaStream_t st) {
+  constexpr int STAGE_BYTES = MB * A_BLK_BYTES + (BN / 64) * B_BLK_BYTES;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert(SMEM <= 227 * 1024, "smem budget");
+  auto kern = pw_gemm_kernel<MB, BN, STAGES, ACC>;
+  SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  kern<<<grid, TC_THREADS, SMEM, st>>>(tw, tx, p);
+  count_launch();
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// Y[N][M][P] = Wp[M x Cin] * X[N][Cin][P]  (+bias)
+int run_pw(const __nv_bfloat16* w, int ld, int transpose, int M, int Cin, const __nv_bfloat16* x,
+           const __nv_bfloat16* bias, __nv_bfloat16* y, int N, int P, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int Mpad = round_up(M, 128), Cpad = round_up(Cin, BK);
+  const size_t need = (size_t)Mpad * Cpad * 2 + 1024;
+  SPC_REQUIRE(ws && ws_bytes >= need, "tcgen05 conv: workspace too small (%zu < %zu)", ws_bytes, need);
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
+  {
+    const int total = Mpad * Cpad;
+    int blocks = (total + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    repack_weights_kernel<<<blocks, 256, 0, st>>>(w, wp, M, Cin, Mpad, Cpad, ld, transpose);
+    count_launch();
+    SPC_CHECK_CUDA(cudaGetLastError());
+  }
+  CUtensorMap tw, tx;
+  {
+    const uint64_t dims[2] = {(uint64_t)Cpad, (uint64_t)Mpad};
+    const uint64_t strides[2] = {0, (uint64_t)Cpad * 2};
+    const uint32_t box[2] = {BK, 128};
+    int rc = make_tmap(&tw, wp, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)P, (uint64_t)Cin, (uint64_t)N};
+    const uint64_t strides[3] = {0, (uint64_t)P * 2, (uint64_t)P * Cin * 2};
+    const uint32_t box[3] = {64, BK, 1};
+    int rc = make_tmap(&tx, x, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  PwParams p{};
+  p.y = y; p.bias = bias; p.M = M; p.Cin = Cin; p.P = P; p.N = N;
+  const int MB = Mpad / 128;
+  p.num_mg = (Mpad + 511) / 512;
+  if (MB == 1) {
+    p.tiles_per_image = (P + 255) / 256; p.num_tiles = p.tiles_per_image * N;
+    return launch_pw<1, 256, 4, 2>(tw, tx, p, st);
+  } else if (MB == 2) {
+    p.tiles_per_image = (P + 127) / 128; p.num_tiles = p.tiles_per_image * N;
+    return launch_pw<2, 128, 4, 2>(tw, tx, p, st);
+  }
+  p.tiles_per_image = (P + 127) / 128; p.num_tiles = p.tiles_per_image * N * p.num_mg;
+  return launch_pw<4, 128, 2, 1>(tw, tx, p, st);
+}
+
+bool pw_shape_ok(const spc_conv_desc* d) {
+  if (d->dtype != SPC_BF16) return false;
+  if (d->R != 1 || d->S != 1 || d->stride_h != 1 || d->stride_w != 1) return false;
+  const long long P = (long long)d->H * d->W;
+  if (P % 8 != 0 || P >= (1ll << 31)) return false;
+  return true;
+}
+
+}  // namespace
+
+bool tc_supported(const spc_conv_desc* d, int op) {
+  if (!pw_shape_ok(d)) return false;
+  if (op == 0 || op == 1) return true;
+  return false;  // wgrad: next
+}
+
+size_t tc_workspace_bytes(const spc_conv_desc* d, int op) {
+  if (op == 0) return (size_t)round_up(d->K, 128) * round_up(d->C, BK) * 2 + 2048;
+  if (op == 1) return (size_t)round_up(d->C, 128) * round_up(d->K, BK) * 2 + 2048;
+  return 0;
+}
+
+int tc_conv_fwd(const spc_conv_desc* d, const void* x, const void* w, const void* bias, void* y, void* ws,
+                size_t ws_bytes, cudaStream_t st) {
+  return run_pw(reinterpret_cast<const __nv_bfloat16*>(w), d->C, 0, d->K, d->C,
+                reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(bias),
+                reinterpret_cast<__nv_bfloat16*>(y), d->N, d->H * d->W, ws, ws_bytes, st);
+}
+
+int tc_conv_dgrad(const spc_conv_desc* d, const void* dy, const void* w, void* dx, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+  // dX[C x P] = W^T[C x K] * dY[K x P]
+  return run_pw(reinterpret_cast<const __nv_bfloat16*>(w), d->C, 1, d->C, d->K,
+                reinterpret_cast<const __nv_bfloat16*>(dy), nullptr, reinterpret_cast<__nv_bfloat16*>(dx), d->N,
+                d->H * d->W, ws, ws_bytes, st);
+}
+
+int tc_conv_wgrad(const spc_conv_desc*, const void*, const void*, float*, int, void*, size_t, cudaStream_t) {
+  set_error("tcgen05 wgrad not built yet");
+  return SPC_EUNSUPPORTED;
+}
+
 }  // namespace spc

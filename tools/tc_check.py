@@ -1,0 +1,66 @@
+"""GPU check of the tcgen05 path against a torch fp32 matmul of the same bf16 inputs (dev tool)."""
+import sys, os, time
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import torch
+from mpi4dl_b200 import _lib
+from mpi4dl_b200.torchgems.spatial import _ConvSpatialFn
+
+torch.manual_seed(0)
+dev = "cuda:0"
+cases = [(64, 128, 16, 16), (104, 208, 32, 64), (208, 52, 64, 64), (52, 208, 24, 40), (416, 416, 32, 32),
+         (1664, 416, 32, 32), (416, 104, 40, 24), (104, 416, 64, 128), (16, 64, 128, 128), (8, 8, 8, 8)]
+if len(sys.argv) > 1 and sys.argv[1] == "big":
+    cases = [(104, 208, 4096, 4096), (208, 52, 4096, 4096), (416, 416, 1024, 1024), (1664, 416, 1024, 1024),
+             (104, 416, 1024, 1024), (416, 104, 1024, 1024), (624, 416, 2048, 2048)]
+ok = True
+for (C, K, H, W) in cases:
+    x = torch.randn(1, C, H, W, device=dev).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(K, C, 1, 1, device=dev) / C ** 0.5).to(torch.bfloat16).requires_grad_(True)
+    b = torch.randn(K, device=dev).to(torch.bfloat16)
+    desc = (1, C, H, W, K, 1, 1, 1, 1, 0, 0, _lib.SPC_BF16, _lib.SPC_ALGO_TCGEN05)
+    y = _ConvSpatialFn.apply(x, w, b, desc, *([None] * 9))
+    torch.cuda.synchronize()
+    if H * W <= 1 << 20:
+        ref = torch.einsum("kc,nchw->nkhw", w.float().view(K, C), x.float()) + b.float().view(1, K, 1, 1)
+        err = (y.float() - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        good = err <= 2e-2 * scale
+        ok &= good
+        print("fwd C=%d K=%d %dx%d  max_err %.4g (scale %.3g) %s" % (C, K, H, W, err, scale, "OK" if good else "FAIL"), flush=True)
+        gy = torch.randn_like(y)
+        # dgrad only (wgrad via direct kernel is slow but fine at these sizes)
+        L = _lib.lib()
+        import ctypes as Cc
+        d = _lib.ConvDesc(*desc)
+        dx = torch.empty_like(x)
+        nb = L.spc_conv_workspace_bytes(Cc.byref(d), 1)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        _lib.check(L.spc_conv2d_dgrad(Cc.byref(d), Cc.c_void_p(gy.data_ptr()), Cc.c_void_p(w.data_ptr()), Cc.c_void_p(dx.data_ptr()),
+                                      Cc.c_void_p(ws.data_ptr()), nb, Cc.c_void_p(torch.cuda.current_stream().cuda_stream)), "dgrad")
+        torch.cuda.synchronize()
+        refdx = torch.einsum("kc,nkhw->nchw", w.float().view(K, C), gy.float())
+        err = (dx.float() - refdx).abs().max().item()
+        scale = refdx.abs().max().item()
+        good = err <= 2e-2 * scale
+        ok &= good
+        print("dgrad                       max_err %.4g (scale %.3g) %s" % (err, scale, "OK" if good else "FAIL"), flush=True)
+    else:
+        # timing
+        with torch.no_grad():
+            for _ in range(3):
+                y = _ConvSpatialFn.apply(x.detach(), w.detach(), None, desc, *([None] * 9))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                y = _ConvSpatialFn.apply(x.detach(), w.detach(), None, desc, *([None] * 9))
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+        byts = (C + K) * H * W * 2
+        fl = 2.0 * C * K * H * W
+        # spot check a slab
+        ref = torch.einsum("kc,nchw->nkhw", w.float().view(K, C), x[:, :, :8].float())
+        err = (y[:, :, :8].float() - ref).abs().max().item()
+        print("fwd C=%d K=%d %dx%d  %.3f ms  %.0f GB/s  %.0f TF/s  spot_err %.3g" % (C, K, H, W, ms, byts / ms / 1e6, fl / ms / 1e9, err), flush=True)
+print("ALL OK" if ok else "SOME FAILED")
