@@ -108,8 +108,9 @@ int spc_conv2d_fwd(const spc_conv_desc* d, const void* x, const spc_halo* halo, 
   const bool any_right = halo->strip[2] || halo->strip[5] || halo->strip[8];
   if (any_top && (rc = fwd_rect(p, d->dtype, 0, top, 0, Wo, st))) return rc;
   if (any_bot && (rc = fwd_rect(p, d->dtype, bot0, Ho, 0, Wo, st))) return rc;
-  if (any_left && (rc = fwd_rect(p, d->dtype, top, bot0, 0, left, st))) return rc;
-  if (any_right && (rc = fwd_rect(p, d->dtype, top, bot0, right0, Wo, st))) return rc;
+  const int sy0 = any_top ? top : 0, sy1 = any_bot ? bot0 : Ho;   // rows not already redone above
+  if (any_left && (rc = fwd_rect(p, d->dtype, sy0, sy1, 0, left, st))) return rc;
+  if (any_right && (rc = fwd_rect(p, d->dtype, sy0, sy1, right0, Wo, st))) return rc;
   return SPC_OK;
 }
 

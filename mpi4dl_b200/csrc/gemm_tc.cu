@@ -73,16 +73,19 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
   return SPC_OK;
 }
 
-// ---- weight repack: Wp[m][c] (bf16, zero padded to [Mpad][Cpad]) --------------------------------
-// transpose == 0: Wp[m][c] = w[m*ld + c]       (fprop: m = out channel K, c = in channel C)
-// transpose == 1: Wp[m][c] = w[c*ld + m]       (dgrad: m = C, c = K)
+// ---- weight repack: Wp[tap][m][c] (bf16, zero padded to [taps][Mpad][Cpad]) -----------------------
+// element = w[m*sm + c*sc + (flip ? taps-1-tap : tap)]
+//   fprop: m = out channel k, c = in channel:  sm = C*RS, sc = RS, flip = 0     (w is [K][C][R][S])
+//   dgrad: m = c, c = k (transposed) and the filter is rotated by 180 degrees:  sm = RS, sc = C*RS, flip = 1
 __global__ void repack_weights_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wp, int M,
-                                      int Cc, int Mpad, int Cpad, int ld, int transpose) {
-  const int total = Mpad * Cpad;
+                                      int Cc, int Mpad, int Cpad, int taps, long long sm, long long sc, int flip) {
+  const int total = taps * Mpad * Cpad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = i % Cpad, m = i / Cpad;
+    const int c = i % Cpad;
+    const int m = (i / Cpad) % Mpad;
+    const int tap = i / (Cpad * Mpad);
     __nv_bfloat16 v = __float2bfloat16(0.f);
-    if (m < M && c < Cc) v = transpose ? w[(size_t)c * ld + m] : w[(size_t)m * ld + c];
+    if (m < M && c < Cc) v = w[(size_t)m * sm + (size_t)c * sc + (flip ? taps - 1 - tap : tap)];
     wp[i] = v;
   }
 }
@@ -103,13 +106,17 @@ struct PwParams {
   int stages;                  // pipeline depth (runtime, <= MAX_STAGES)
   int wres;                    // 1: all weight chunks stay resident in smem (loaded once per CTA)
   int out_bufs;                // 1 or 2 epilogue staging buffers
+  int taps, S, ph, pw;         // filter taps (R*S), filter width, zero padding (tap mode)
+  int W, Mpad;                 // image width (tap mode: tiles are 64-pixel row segments), padded M
+  int shiftN;                  // N when the activations are S column-shifted copies (S > 1), else 0
   const __nv_bfloat16* bias;   // [M] or null
 };
 
 template <int MB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-               const __grid_constant__ CUtensorMap tmap_y, const PwParams p) {
+               const __grid_constant__ CUtensorMap tmap_x4, const __grid_constant__ CUtensorMap tmap_y,
+               const PwParams p) {
   constexpr int NB = BN / 64;
   constexpr int ACC = (MB <= 2) ? 2 : 1;
   static_assert(ACC * MB * BN <= TMEM_COLS, "TMEM budget");
@@ -117,7 +124,8 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int kchunks = (p.Cin + BK - 1) / BK;
   const int ksteps_total = (p.Cin + 15) / 16;
-  const int wres_bytes = p.wres ? kchunks * MB * A_BLK_BYTES : 0;
+  const int iters = p.taps * kchunks;      // K loop: (filter tap, 64-channel chunk)
+  const int wres_bytes = p.wres ? iters * MB * A_BLK_BYTES : 0;
   const int stage_bytes = (p.wres ? 0 : MB * A_BLK_BYTES) + NB * B_BLK_BYTES;
   uint8_t* wres = smem;
   uint8_t* stage0 = smem + wres_bytes;
@@ -150,11 +158,11 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       tma_prefetch_desc(&tmap_x);
       if (p.wres) {   // weights-stationary: every CTA keeps the whole (padded) filter in smem
         mbar_arrive_expect_tx(wfull, wres_bytes);
-        const int mg0 = 0;  // wres implies num_mg == 1
-        for (int kc = 0; kc < kchunks; ++kc)
+        for (int it = 0; it < iters; ++it)   // wres implies num_mg == 1
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb)
-            tma_load_2d(wres + (kc * MB + mb) * A_BLK_BYTES, &tmap_w, wfull, kc * BK, mg0 * 512 + mb * 128);
+            tma_load_2d(wres + (it * MB + mb) * A_BLK_BYTES, &tmap_w, wfull, (it % kchunks) * BK,
+                        (it / kchunks) * p.Mpad + mb * 128);
       }
       int s = 0, ph = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -162,18 +170,30 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const int tt = t / p.num_mg;
         const int n = tt / p.tiles_per_image;
         const int p0 = (tt % p.tiles_per_image) * BN;
-        for (int kc = 0; kc < kchunks; ++kc) {
+        for (int it = 0; it < iters; ++it) {
+          const int kc = it % kchunks, tap = it / kchunks;
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = stage0 + s * stage_bytes;
           mbar_arrive_expect_tx(&full[s], stage_bytes);
           if (!p.wres) {
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb)
-              tma_load_2d(st + mb * A_BLK_BYTES, &tmap_w, &full[s], kc * BK, mg * 512 + mb * 128);
+              tma_load_2d(st + mb * A_BLK_BYTES, &tmap_w, &full[s], kc * BK, tap * p.Mpad + mg * 512 + mb * 128);
             st += MB * A_BLK_BYTES;
           }
+          if (p.taps == 1) {
 #pragma unroll
-          for (int j = 0; j < NB; ++j) tma_load_3d(st + j * B_BLK_BYTES, &tmap_x, &full[s], p0 + j * 64, kc * BK, n);
+            for (int j = 0; j < NB; ++j) tma_load_3d(st + j * B_BLK_BYTES, &tmap_x, &full[s], p0 + j * 64, kc * BK, n);
+          } else {
+            // shifted window of this tap; out-of-image rows / columns are zero-filled by TMA (= zero padding)
+            const int dr = tap / p.S - p.ph;
+            const int img = n + (tap % p.S) * p.shiftN;   // column shift = which pre-shifted copy
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+              const int q = p0 + j * 64, hq = q / p.W, wq = q - hq * p.W;
+              tma_load_4d(st + j * B_BLK_BYTES, &tmap_x4, &full[s], wq, hq + dr, kc * BK, img);
+            }
+          }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -187,11 +207,12 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         mbar_wait(&tempty[a], aph ^ 1);
         tc_fence_after();
-        for (int kc = 0; kc < kchunks; ++kc) {
+        for (int it = 0; it < iters; ++it) {
+          const int kc = it % kchunks;
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t st = smem_u32(stage0 + s * stage_bytes);
-          const uint32_t sa = p.wres ? smem_u32(wres + kc * MB * A_BLK_BYTES) : st;
+          const uint32_t sa = p.wres ? smem_u32(wres + it * MB * A_BLK_BYTES) : st;
           const uint32_t sb = p.wres ? st : st + MB * A_BLK_BYTES;
           const int nsteps = min(4, ksteps_total - kc * 4);
           for (int ks = 0; ks < nsteps; ++ks) {
@@ -201,11 +222,11 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             for (int mb = 0; mb < MB; ++mb) {
               // A: K-major SW128. 8-row groups at SBO = 1024 B; +32 B per 16-channel k-step
               const uint64_t adesc = umma_desc(sa + mb * A_BLK_BYTES + ks * 32, 16, 1024);
-              umma_bf16(tmem_base + (a * MB + mb) * BN, adesc, bdesc, IDESC, (kc | ks) ? 1u : 0u);
+              umma_bf16(tmem_base + (a * MB + mb) * BN, adesc, bdesc, IDESC, (it | ks) ? 1u : 0u);
             }
           }
           umma_commit(&empty[s]);
-          if (kc == kchunks - 1) umma_commit(&tfull[a]);
+          if (it == iters - 1) umma_commit(&tfull[a]);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         if (++a == ACC) { a = 0; aph ^= 1; }
@@ -278,10 +299,11 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int SMEM_AUX = 1024 /*align*/ + 512 /*barriers*/;
 
 template <int MB>
-int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, PwParams p, cudaStream_t st) {
+int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& tx4, const CUtensorMap& ty, PwParams p,
+              cudaStream_t st) {
   const int kchunks = (p.Cin + BK - 1) / BK;
   const int budget = SMEM_LIMIT - SMEM_AUX;
-  const int wres_bytes = kchunks * MB * A_BLK_BYTES;
+  const int wres_bytes = p.taps * kchunks * MB * A_BLK_BYTES;
   p.wres = (p.num_mg == 1 && wres_bytes <= 128 * 1024) ? 1 : 0;
   const int stage_bytes = (p.wres ? 0 : MB * A_BLK_BYTES) + (BN / 64) * B_BLK_BYTES;
   const int rem = budget - (p.wres ? wres_bytes : 0);
@@ -297,7 +319,7 @@ int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& t
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  kern<<<grid, TC_THREADS, smem, st>>>(tw, tx, ty, p);
+  kern<<<grid, TC_THREADS, smem, st>>>(tw, tx, tx4, ty, p);
   count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
@@ -312,42 +334,88 @@ int make_act_tmap(CUtensorMap* m, const void* base, int P, int Cc, int N, int bo
   return make_tmap(m, base, 3, dims, strides, box);
 }
 
-// Y[N][M][P] = Wp[M x Cin] * X[N][Cin][P]  (+bias)
-int run_pw(const __nv_bfloat16* w, int ld, int transpose, int M, int Cin, const __nv_bfloat16* x,
-           const __nv_bfloat16* bias, __nv_bfloat16* y, int N, int P, void* ws, size_t ws_bytes, cudaStream_t st) {
-  const int Mpad = round_up(M, 128), Cpad = round_up(Cin, BK);
-  const size_t need = (size_t)Mpad * Cpad * 2 + 1024;
+int launch_shift_copies(const void* x, void* xs, size_t planes, int H, int W, int S, int pw, cudaStream_t st);
+
+// Geometry of one tcgen05 convolution launch (fprop, or dgrad expressed as a convolution of dY).
+struct TcConv {
+  const __nv_bfloat16* w;      // original filter [K][C][R][S]
+  long long sm, sc;            // strides of (output channel m, reduction channel c) in w
+  int flip;                    // rotate taps by 180 degrees (dgrad)
+  int M, Cin;                  // output channels, reduction channels
+  int R, S, ph, pw;            // filter and zero padding
+  int H, W, N;                 // image (stride 1: output extent == input extent)
+};
+
+// Y[N][M][H*W] = sum_taps Wp[tap][M x Cin] * shift_tap(X[N][Cin][H][W])  (+bias)
+int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bias, __nv_bfloat16* y, void* ws,
+                size_t ws_bytes, cudaStream_t st) {
+  const int taps = c.R * c.S;
+  const int P = c.H * c.W;
+  const int Mpad = round_up(c.M, 128), Cpad = round_up(c.Cin, BK);
+  const uintptr_t ws0 = reinterpret_cast<uintptr_t>(ws);
+  const uintptr_t wp_addr = (ws0 + 1023) & ~(uintptr_t)1023;
+  const uintptr_t xs_addr = (wp_addr + (size_t)taps * Mpad * Cpad * 2 + 1023) & ~(uintptr_t)1023;
+  const size_t xs_bytes = c.S > 1 ? (size_t)c.S * c.N * c.Cin * P * 2 : 0;
+  const size_t need = (xs_addr - ws0) + xs_bytes;
   SPC_REQUIRE(ws && ws_bytes >= need, "tcgen05 conv: workspace too small (%zu < %zu)", ws_bytes, need);
-  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(wp_addr);
+  const __nv_bfloat16* xsrc = x;
+  if (c.S > 1) {
+    void* xs = reinterpret_cast<void*>(xs_addr);
+    int rc0 = launch_shift_copies(x, xs, (size_t)c.N * c.Cin, c.H, c.W, c.S, c.pw, st);
+    if (rc0) return rc0;
+    xsrc = reinterpret_cast<const __nv_bfloat16*>(xs);
+  }
   {
-    const int total = Mpad * Cpad;
+    const int total = taps * Mpad * Cpad;
     int blocks = (total + 255) / 256;
-    if (blocks > 592) blocks = 592;
-    repack_weights_kernel<<<blocks, 256, 0, st>>>(w, wp, M, Cin, Mpad, Cpad, ld, transpose);
+    if (blocks > 1184) blocks = 1184;
+    repack_weights_kernel<<<blocks, 256, 0, st>>>(c.w, wp, c.M, c.Cin, Mpad, Cpad, taps, c.sm, c.sc, c.flip);
     count_launch();
     SPC_CHECK_CUDA(cudaGetLastError());
   }
-  CUtensorMap tw, tx, ty;
+  CUtensorMap tw, tx, tx4, ty;
   {
-    const uint64_t dims[2] = {(uint64_t)Cpad, (uint64_t)Mpad};
+    const uint64_t dims[2] = {(uint64_t)Cpad, (uint64_t)taps * Mpad};
     const uint64_t strides[2] = {0, (uint64_t)Cpad * 2};
     const uint32_t box[2] = {BK, 128};
     int rc = make_tmap(&tw, wp, 2, dims, strides, box);
     if (rc) return rc;
   }
-  int rc = make_act_tmap(&tx, x, P, Cin, N, BK);
+  int rc = make_act_tmap(&tx, x, P, c.Cin, c.N, BK);
   if (rc) return rc;
-  rc = make_act_tmap(&ty, y, P, M, N, 128);
+  if (taps > 1) {
+    const uint64_t dims[4] = {(uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.Cin, (uint64_t)c.N * c.S};
+    const uint64_t strides[4] = {0, (uint64_t)c.W * 2, (uint64_t)P * 2, (uint64_t)P * c.Cin * 2};
+    const uint32_t box[4] = {64, 1, BK, 1};
+    rc = make_tmap(&tx4, xsrc, 4, dims, strides, box);
+    if (rc) return rc;
+  } else {
+    tx4 = tx;
+  }
+  rc = make_act_tmap(&ty, y, P, c.M, c.N, 128);
   if (rc) return rc;
   PwParams p{};
-  p.bias = bias; p.M = M; p.Cin = Cin; p.P = P; p.N = N;
+  p.bias = bias; p.M = c.M; p.Cin = c.Cin; p.P = P; p.N = c.N;
+  p.taps = taps; p.S = c.S; p.ph = c.ph; p.pw = c.pw; p.W = c.W; p.Mpad = Mpad;
+  p.shiftN = c.S > 1 ? c.N : 0;
   const int MBtot = Mpad / 128;
   p.num_mg = (Mpad + 511) / 512;
   p.tiles_per_image = (P + BN - 1) / BN;
-  p.num_tiles = p.tiles_per_image * N * p.num_mg;
-  if (MBtot == 1) return launch_pw<1>(tw, tx, ty, p, st);
-  if (MBtot == 2) return launch_pw<2>(tw, tx, ty, p, st);
-  return launch_pw<4>(tw, tx, ty, p, st);
+  p.num_tiles = p.tiles_per_image * c.N * p.num_mg;
+  if (MBtot == 1) return launch_pw<1>(tw, tx, tx4, ty, p, st);
+  if (MBtot == 2) return launch_pw<2>(tw, tx, tx4, ty, p, st);
+  return launch_pw<4>(tw, tx, tx4, ty, p, st);
+}
+
+// pointwise helper (1x1): Y[N][M][P] = Wp[M x Cin] * X[N][Cin][P]
+int run_pw(const __nv_bfloat16* w, int ld, int transpose, int M, int Cin, const __nv_bfloat16* x,
+           const __nv_bfloat16* bias, __nv_bfloat16* y, int N, int P, void* ws, size_t ws_bytes, cudaStream_t st) {
+  TcConv c{};
+  c.w = w;
+  c.sm = transpose ? 1 : ld; c.sc = transpose ? ld : 1; c.flip = 0;
+  c.M = M; c.Cin = Cin; c.R = 1; c.S = 1; c.ph = 0; c.pw = 0; c.H = 1; c.W = P; c.N = N;
+  return run_conv_tc(c, x, bias, y, ws, ws_bytes, st);
 }
 
 // ---- wgrad kernel: dW[K x C] += dY[K x P] * X[C x P]^T --------------------------------------------
@@ -530,10 +598,115 @@ int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K,
   return launch_wg<4>(tdy, tx, p, st);
 }
 
+// ---- stride-2 pointwise convs: subsample / zero-upsample passes around the GEMM ------------------
+// y[n,c,i,j] = x[n,c,2i,2j]; 8 outputs per thread (two 16-byte loads, one 16-byte store)
+__global__ void subsample2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t planes,
+                                  int H, int W) {
+  const int Ho = H / 2, Wo = W / 2, wv = Wo / 8;
+  const size_t total = planes * Ho * wv;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % wv);
+    const int oy = (int)((i / wv) % Ho);
+    const size_t pl = i / ((size_t)wv * Ho);
+    const uint4* src = reinterpret_cast<const uint4*>(x + (pl * H + 2 * oy) * W + v * 16);
+    const uint4 a = __ldg(src), b = __ldg(src + 1);
+    uint4 o;
+    o.x = __byte_perm(a.x, a.y, 0x5410);
+    o.y = __byte_perm(a.z, a.w, 0x5410);
+    o.z = __byte_perm(b.x, b.y, 0x5410);
+    o.w = __byte_perm(b.z, b.w, 0x5410);
+    *reinterpret_cast<uint4*>(y + (pl * Ho + oy) * Wo + v * 8) = o;
+  }
+}
+// dx[n,c,2i,2j] = g[n,c,i,j], zero elsewhere
+__global__ void upsample2_zero_kernel(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dx,
+                                      size_t planes, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2, wv = Wo / 8;
+  const size_t total = planes * Ho * wv;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % wv);
+    const int oy = (int)((i / wv) % Ho);
+    const size_t pl = i / ((size_t)wv * Ho);
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(g + (pl * Ho + oy) * Wo + v * 8));
+    uint4 lo, hi;   // element e -> position 2e, zeros between
+    lo.x = a.x & 0xFFFFu; lo.y = a.x >> 16; lo.z = a.y & 0xFFFFu; lo.w = a.y >> 16;
+    hi.x = a.z & 0xFFFFu; hi.y = a.z >> 16; hi.z = a.w & 0xFFFFu; hi.w = a.w >> 16;
+    uint4* d0 = reinterpret_cast<uint4*>(dx + (pl * H + 2 * oy) * W + v * 16);
+    uint4* d1 = reinterpret_cast<uint4*>(dx + (pl * H + 2 * oy + 1) * W + v * 16);
+    d0[0] = lo; d0[1] = hi; d1[0] = z; d1[1] = z;
+  }
+}
+int launch_resample(bool up, const void* src, void* dst, size_t planes, int H, int W, cudaStream_t st) {
+  const size_t total = planes * (H / 2) * (W / 16);
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (up)
+    upsample2_zero_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, planes, H, W);
+  else
+    subsample2_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, planes, H, W);
+  count_launch();
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+// TMA tile loads need 16-byte aligned inner coordinates (measured: tools/tma_probe.cu), so the
+// horizontal taps of an R x S filter cannot be fetched as shifted boxes.  For S > 1 one pre-pass
+// writes the S column-shifted, zero-filled copies  xs[s][plane][h][w] = x[plane][h][w + s - pw];
+// every tap (r, s) is then an ALIGNED box of copy s at row offset r - ph.
+__global__ void shift_copies_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xs,
+                                    size_t planes, int H, int W, int S, int pw) {
+  const int wv = W / 8;
+  const size_t rows = planes * H;
+  const size_t total = rows * wv * S;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % wv);
+    const size_t row = (i / wv) % rows;
+    const int sidx = (int)(i / ((size_t)wv * rows));
+    const __nv_bfloat16* src = x + row * W;
+    const int w0 = v * 8 + sidx - pw;
+    __nv_bfloat16 e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int w = w0 + j;
+      e[j] = ((unsigned)w < (unsigned)W) ? src[w] : __float2bfloat16(0.f);
+    }
+    *reinterpret_cast<uint4*>(xs + ((size_t)sidx * rows + row) * W + v * 8) = *reinterpret_cast<const uint4*>(e);
+  }
+}
+int launch_shift_copies(const void* x, void* xs, size_t planes, int H, int W, int S, int pw, cudaStream_t st) {
+  const size_t total = planes * H * (W / 8) * S;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  shift_copies_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)xs, planes, H, W, S, pw);
+  count_launch();
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+inline bool is_s2(const spc_conv_desc* d) { return d->stride_h == 2 && d->stride_w == 2; }
+inline size_t align1k(size_t b) { return (b + 1023) & ~(size_t)1023; }
+
+bool tap_shape_ok(const spc_conv_desc* d) {   // RxS stride-1 "same" convs on 64-pixel row segments
+  if (d->dtype != SPC_BF16) return false;
+  if (d->R * d->S == 1 || d->R * d->S > 49) return false;
+  if (d->stride_h != 1 || d->stride_w != 1) return false;
+  if (d->W % 64 != 0) return false;
+  if ((size_t)d->S * d->N * (d->C > d->K ? d->C : d->K) * d->H * d->W * 2 > (8ull << 30)) return false;
+  if ((d->R & 1) == 0 || (d->S & 1) == 0) return false;
+  return (long long)d->H * d->W < (1ll << 31);
+}
+
 bool pw_shape_ok(const spc_conv_desc* d) {
   if (d->dtype != SPC_BF16) return false;
-  if (d->R != 1 || d->S != 1 || d->stride_h != 1 || d->stride_w != 1) return false;
-  const long long P = (long long)d->H * d->W;
+  if (d->R != 1 || d->S != 1) return false;
+  long long P = (long long)d->H * d->W;
+  if (is_s2(d)) {
+    if (d->H % 2 || d->W % 32) return false;   // 16-byte vectors on both sides of the resample
+    P /= 4;
+  } else if (d->stride_h != 1 || d->stride_w != 1) {
+    return false;
+  }
   if (P % 8 != 0 || P >= (1ll << 31)) return false;
   return true;
 }
@@ -541,18 +714,46 @@ bool pw_shape_ok(const spc_conv_desc* d) {
 }  // namespace
 
 bool tc_supported(const spc_conv_desc* d, int op) {
-  if (!pw_shape_ok(d)) return false;
-  return true;
+  if (pw_shape_ok(d)) return true;
+  if (tap_shape_ok(d)) return op != 2;   // multi-tap wgrad: next
+  return false;
 }
 
-size_t tc_workspace_bytes(const spc_conv_desc* d, int op) {
-  if (op == 0) return (size_t)round_up(d->K, 128) * round_up(d->C, BK) * 2 + 2048;
-  if (op == 1) return (size_t)round_up(d->C, 128) * round_up(d->K, BK) * 2 + 2048;
+// workspace = [repacked weights | subsampled activations (stride-2 only)]
+static size_t wbytes(const spc_conv_desc* d, int op) {
+  const size_t taps = (size_t)d->R * d->S;
+  if (op == 0) return align1k(taps * round_up(d->K, 128) * round_up(d->C, BK) * 2 + 1024);
+  if (op == 1) return align1k(taps * round_up(d->C, 128) * round_up(d->K, BK) * 2 + 1024);
   return 0;
+}
+size_t tc_workspace_bytes(const spc_conv_desc* d, int op) {
+  size_t b = wbytes(d, op);
+  if (d->S > 1 && op < 2)   // S column-shifted copies of the conv input (x for fprop, dy for dgrad)
+    b += align1k((size_t)d->S * d->N * (op == 0 ? d->C : d->K) * d->H * d->W * 2) + 2048;
+  if (is_s2(d)) b += align1k((size_t)d->N * d->C * (d->H / 2) * (d->W / 2) * 2) + 1024;
+  return b + 1024;
 }
 
 int tc_conv_fwd(const spc_conv_desc* d, const void* x, const void* w, const void* bias, void* y, void* ws,
                 size_t ws_bytes, cudaStream_t st) {
+  SPC_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(d, 0), "tcgen05 conv: workspace too small");
+  if (d->R * d->S > 1) {
+    TcConv c{};
+    c.w = reinterpret_cast<const __nv_bfloat16*>(w);
+    c.sm = (long long)d->C * d->R * d->S; c.sc = (long long)d->R * d->S; c.flip = 0;
+    c.M = d->K; c.Cin = d->C; c.R = d->R; c.S = d->S; c.ph = d->pad_h; c.pw = d->pad_w;
+    c.H = d->H; c.W = d->W; c.N = d->N;
+    return run_conv_tc(c, reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(bias),
+                       reinterpret_cast<__nv_bfloat16*>(y), ws, ws_bytes, st);
+  }
+  if (is_s2(d)) {   // Y = W * subsample(X)
+    void* xs = reinterpret_cast<void*>(align1k(reinterpret_cast<uintptr_t>(ws) + wbytes(d, 0)));
+    int rc = launch_resample(false, x, xs, (size_t)d->N * d->C, d->H, d->W, st);
+    if (rc) return rc;
+    return run_pw(reinterpret_cast<const __nv_bfloat16*>(w), d->C, 0, d->K, d->C,
+                  reinterpret_cast<const __nv_bfloat16*>(xs), reinterpret_cast<const __nv_bfloat16*>(bias),
+                  reinterpret_cast<__nv_bfloat16*>(y), d->N, (d->H / 2) * (d->W / 2), ws, wbytes(d, 0), st);
+  }
   return run_pw(reinterpret_cast<const __nv_bfloat16*>(w), d->C, 0, d->K, d->C,
                 reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(bias),
                 reinterpret_cast<__nv_bfloat16*>(y), d->N, d->H * d->W, ws, ws_bytes, st);
@@ -561,15 +762,41 @@ int tc_conv_fwd(const spc_conv_desc* d, const void* x, const void* w, const void
 int tc_conv_dgrad(const spc_conv_desc* d, const void* dy, const void* w, void* dx, void* ws, size_t ws_bytes,
                   cudaStream_t st) {
   // dX[C x P] = W^T[C x K] * dY[K x P]
+  SPC_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(d, 1), "tcgen05 conv: workspace too small");
+  if (d->R * d->S > 1) {   // stride-1 dgrad = correlation of dY with the transposed, 180-degree rotated filter
+    TcConv c{};
+    c.w = reinterpret_cast<const __nv_bfloat16*>(w);
+    c.sm = (long long)d->R * d->S; c.sc = (long long)d->C * d->R * d->S; c.flip = 1;
+    c.M = d->C; c.Cin = d->K; c.R = d->R; c.S = d->S; c.ph = d->R - 1 - d->pad_h; c.pw = d->S - 1 - d->pad_w;
+    c.H = d->H; c.W = d->W; c.N = d->N;
+    return run_conv_tc(c, reinterpret_cast<const __nv_bfloat16*>(dy), nullptr, reinterpret_cast<__nv_bfloat16*>(dx), ws,
+                       ws_bytes, st);
+  }
+  if (is_s2(d)) {   // dX = zero_upsample(W^T * dY)
+    void* gs = reinterpret_cast<void*>(align1k(reinterpret_cast<uintptr_t>(ws) + wbytes(d, 1)));
+    int rc = run_pw(reinterpret_cast<const __nv_bfloat16*>(w), d->C, 1, d->C, d->K,
+                    reinterpret_cast<const __nv_bfloat16*>(dy), nullptr, reinterpret_cast<__nv_bfloat16*>(gs), d->N,
+                    (d->H / 2) * (d->W / 2), ws, wbytes(d, 1), st);
+    if (rc) return rc;
+    return launch_resample(true, gs, dx, (size_t)d->N * d->C, d->H, d->W, st);
+  }
   return run_pw(reinterpret_cast<const __nv_bfloat16*>(w), d->C, 1, d->C, d->K,
                 reinterpret_cast<const __nv_bfloat16*>(dy), nullptr, reinterpret_cast<__nv_bfloat16*>(dx), d->N,
                 d->H * d->W, ws, ws_bytes, st);
 }
 
-int tc_conv_wgrad(const spc_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, void*, size_t,
-                  cudaStream_t st) {
+int tc_conv_wgrad(const spc_conv_desc* d, const void* x, const void* dy, float* dw, int accumulate, void* ws,
+                  size_t ws_bytes, cudaStream_t st) {
   // the kernel accumulates with atomics; api.cu has already zeroed dw when !accumulate
   (void)accumulate;
+  if (is_s2(d)) {
+    SPC_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(d, 2), "tcgen05 wgrad: workspace too small");
+    void* xs = reinterpret_cast<void*>(align1k(reinterpret_cast<uintptr_t>(ws)));
+    int rc = launch_resample(false, x, xs, (size_t)d->N * d->C, d->H, d->W, st);
+    if (rc) return rc;
+    return run_wgrad(reinterpret_cast<const __nv_bfloat16*>(xs), reinterpret_cast<const __nv_bfloat16*>(dy), dw, d->K,
+                     d->C, d->N, (d->H / 2) * (d->W / 2), st);
+  }
   return run_wgrad(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), dw, d->K,
                    d->C, d->N, d->H * d->W, st);
 }

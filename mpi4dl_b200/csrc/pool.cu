@@ -160,6 +160,104 @@ __global__ void pool_bwd_kernel(const PoolParams p) {
   }
 }
 
+template <typename T, int NEL>
+__device__ __forceinline__ void load_vec(const T* __restrict__ src, float (&dst)[NEL]) {
+  constexpr int NV = NEL * sizeof(T) / 16;
+  uint4 raw[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) raw[q] = __ldg(reinterpret_cast<const uint4*>(src) + q);
+  const T* e = reinterpret_cast<const T*>(raw);
+#pragma unroll
+  for (int j = 0; j < NEL; ++j) dst[j] = to_f32<T>(e[j]);
+}
+template <typename T, int NEL>
+__device__ __forceinline__ void store_vec(T* __restrict__ dst, const float (&src)[NEL]) {
+  constexpr int NV = NEL * sizeof(T) / 16;
+  uint4 raw[NV];
+  T* e = reinterpret_cast<T*>(raw);
+#pragma unroll
+  for (int j = 0; j < NEL; ++j) e[j] = from_f32<T>(src[j]);
+#pragma unroll
+  for (int q = 0; q < NV; ++q) reinterpret_cast<uint4*>(dst)[q] = raw[q];
+}
+
+// ---- backward, vectorised stride-2 paths (no halos, W % 16 == 0) -------------------------------
+// One thread owns 8 consecutive outputs (oy, ox0..ox0+7) and writes the 2 x 16 input-gradient
+// elements of rows 2*oy, 2*oy+1 as 16-byte vectors.
+//  avg 3x3 s2 pad 1: dx[2m,2n]=g[m,n]; dx[2m,2n+1]=g[m,n]+g[m,n+1]; dx[2m+1,2n]=g[m,n]+g[m+1,n];
+//                    dx[2m+1,2n+1]=g[m,n]+g[m,n+1]+g[m+1,n]+g[m+1,n+1]   (all / 9)
+//  max 2x2 s2:       dx = g at the first maximal element of each window, else 0
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+pool_bwd_s2_vec_kernel(const PoolParams p) {
+  constexpr int V = 8;
+  const int H = p.in.H, W = p.in.W, Ho = p.Ho, Wo = p.Wo;
+  const int wv = Wo / V;
+  const size_t total = (size_t)p.in.N * p.in.C * Ho * wv;
+  const T* dy = reinterpret_cast<const T*>(p.dy);
+  const T* x = reinterpret_cast<const T*>(p.in.x);
+  T* dx = reinterpret_cast<T*>(p.out);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int vx = (int)(i % wv);
+    const int oy = (int)((i / wv) % Ho);
+    const size_t nc = i / ((size_t)wv * Ho);
+    const int ox0 = vx * V;
+    const T* g0 = dy + (nc * Ho + oy) * Wo + ox0;
+    float g[V + 1], gn[V + 1];
+    {
+      float gv[V];
+      load_vec<T, V>(g0, gv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) g[j] = gv[j];
+    }
+    float o0[2 * V], o1[2 * V];
+    if (MODE == SPC_POOL_AVG) {
+      const bool has_r = ox0 + V < Wo, has_d = oy + 1 < Ho;
+      g[V] = has_r ? to_f32<T>(g0[V]) : 0.f;
+      if (has_d) {
+        float gv[V];
+        load_vec<T, V>(g0 + Wo, gv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) gn[j] = gv[j];
+        gn[V] = has_r ? to_f32<T>(g0[Wo + V]) : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j <= V; ++j) gn[j] = 0.f;
+      }
+      const float inv = 1.f / 9.f;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        o0[2 * j] = g[j] * inv;
+        o0[2 * j + 1] = (g[j] + g[j + 1]) * inv;
+        o1[2 * j] = (g[j] + gn[j]) * inv;
+        o1[2 * j + 1] = (g[j] + g[j + 1] + gn[j] + gn[j + 1]) * inv;
+      }
+    } else {
+      const T* x0 = x + (nc * H + 2 * oy) * W + 2 * ox0;
+      float r0[2 * V], r1[2 * V];
+      load_vec<T, 2 * V>(x0, r0);
+      load_vec<T, 2 * V>(x0 + W, r1);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float a = r0[2 * j], b = r0[2 * j + 1];
+        const float c = r1[2 * j], d = r1[2 * j + 1];
+        int best = 0;
+        float m = a;
+        if (b > m) { m = b; best = 1; }
+        if (c > m) { m = c; best = 2; }
+        if (d > m) { m = d; best = 3; }
+        o0[2 * j] = best == 0 ? g[j] : 0.f;
+        o0[2 * j + 1] = best == 1 ? g[j] : 0.f;
+        o1[2 * j] = best == 2 ? g[j] : 0.f;
+        o1[2 * j + 1] = best == 3 ? g[j] : 0.f;
+      }
+    }
+    T* d0 = dx + (nc * H + 2 * oy) * W + 2 * ox0;
+    store_vec<T, 2 * V>(d0, o0);
+    store_vec<T, 2 * V>(d0 + W, o1);
+  }
+}
+
 template <typename T>
 int run_fwd(const PoolParams& p, cudaStream_t st) {
   const size_t total = (size_t)p.in.N * p.in.C * p.Ho * p.Wo;
@@ -190,7 +288,28 @@ int run_bwd(const PoolParams& p, cudaStream_t st) {
   const size_t total = (size_t)p.in.N * p.in.C * p.in.H * p.in.W;
   if (total == 0) return SPC_OK;
   const int blocks = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
-  pool_bwd_kernel<T><<<blocks, 256, 0, st>>>(p);
+  const bool aligned = ((uintptr_t)p.in.x % 16 == 0) && ((uintptr_t)p.out % 16 == 0) && ((uintptr_t)p.dy % 16 == 0);
+  const bool even = aligned && p.in.W % 16 == 0 && p.in.H % 2 == 0 && p.in.W == 2 * p.Wo && p.in.H == 2 * p.Ho;
+  if (p.mode == SPC_POOL_AVG && p.k == 3 && p.stride == 1 && aligned && p.in.W % (16 / sizeof(T)) == 0) {
+    // avg 3x3 s1: dx = avgpool3x3(dy) with zero padding -- the forward kernel on dy, no halos
+    PoolParams q = p;
+    q.in = make_view(p.dy, nullptr, p.in.N, p.in.C, p.Ho, p.Wo, 1, 1);
+    q.dy = nullptr;
+    constexpr int VEC = 16 / sizeof(T);
+    const size_t vt = total / VEC;
+    const int b2 = (int)((vt + 255) / 256 > 148 * 32 ? 148 * 32 : (vt + 255) / 256);
+    pool_fwd_vec_kernel<T, VEC, 3, 1><<<b2, 256, 0, st>>>(q);
+  } else if (even && p.mode == SPC_POOL_AVG && p.k == 3 && p.stride == 2) {
+    const size_t vt = total / 32;
+    const int b2 = (int)((vt + 255) / 256 > 148 * 32 ? 148 * 32 : (vt + 255) / 256);
+    pool_bwd_s2_vec_kernel<T, SPC_POOL_AVG><<<b2, 256, 0, st>>>(p);
+  } else if (even && p.mode == SPC_POOL_MAX && p.k == 2 && p.stride == 2) {
+    const size_t vt = total / 32;
+    const int b2 = (int)((vt + 255) / 256 > 148 * 32 ? 148 * 32 : (vt + 255) / 256);
+    pool_bwd_s2_vec_kernel<T, SPC_POOL_MAX><<<b2, 256, 0, st>>>(p);
+  } else {
+    pool_bwd_kernel<T><<<blocks, 256, 0, st>>>(p);
+  }
   spc::count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;

@@ -142,6 +142,14 @@ CONV_CASES = [
     (64, 128, (1, 1), (2, 2), 16, 32, False),
     (5, 7, (5, 5), (1, 1), 12, 12, True),
     (17, 19, (3, 3), (1, 1), 7, 5, True),         # odd everything, tile smaller than a CTA tile
+    # shapes that take the tcgen05 path in bf16 (W % 64 == 0 for multi-tap, H*W % 8 == 0 for 1x1)
+    (52, 52, (1, 7), (1, 1), 8, 128, False),
+    (104, 104, (7, 1), (1, 1), 16, 64, False),
+    (64, 16, (3, 3), (1, 1), 12, 192, True),
+    (104, 104, (3, 3), (1, 1), 9, 64, False),
+    (1664, 416, (1, 1), (1, 1), 8, 48, False),    # 4 M-blocks, streamed weights
+    (416, 1248, (1, 1), (1, 1), 8, 32, False),    # > 512 output channels: M groups
+    (104, 208, (1, 1), (2, 2), 16, 64, False),    # stride-2 pointwise (FactorizedReduce)
 ]
 
 

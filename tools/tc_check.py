@@ -98,4 +98,47 @@ for (C, K, H, W) in cases:
         refdw = torch.einsum("nkhw,nchw->kc", gy[:, :, :64].float(), x[:, :, :64].float())
         # full check of wgrad on a cropped problem is not possible; check dw magnitude sanity only
         print("   dw abs max %.3g" % dw.abs().max().item(), flush=True)
+# multi-tap convs vs cuDNN fp32 (dev check only)
+import torch.nn.functional as F
+taps = [(52, 52, 1, 7, 32, 128), (104, 104, 7, 1, 32, 64), (104, 104, 3, 3, 16, 128), (64, 16, 3, 3, 8, 192)]
+if len(sys.argv) > 1 and sys.argv[1] == "big":
+    taps = [(104, 104, 1, 7, 1024, 1024), (104, 104, 7, 1, 1024, 1024), (52, 52, 1, 7, 2048, 2048), (64, 16, 3, 3, 4096, 4096)]
+torch.backends.cudnn.allow_tf32 = False
+for (C, K, R, S, H, W) in taps:
+    x = torch.randn(1, C, H, W, device=dev).to(torch.bfloat16)
+    w = (torch.randn(K, C, R, S, device=dev) / (C * R * S) ** 0.5).to(torch.bfloat16)
+    desc = (1, C, H, W, K, R, S, 1, 1, (R - 1) // 2, (S - 1) // 2, _lib.SPC_BF16, _lib.SPC_ALGO_TCGEN05)
+    with torch.no_grad():
+        y = _ConvSpatialFn.apply(x, w, None, desc, *([None] * 9))
+        torch.cuda.synchronize()
+        hs = min(H, 64)
+        ref = F.conv2d(x[:, :, :hs + R].float(), w.float(), None, 1, ((R - 1) // 2, (S - 1) // 2))[:, :, :hs]
+        err = (y[:, :, :hs].float() - ref).abs().max().item()
+        scale = ref.abs().max().item()
+        good = err <= 2e-2 * scale
+        ok &= good
+        import ctypes as Cc
+        L = _lib.lib(); d = _lib.ConvDesc(*desc)
+        gy = torch.randn_like(y); dx = torch.empty_like(x)
+        nb1 = L.spc_conv_workspace_bytes(Cc.byref(d), 1)
+        ws = torch.empty(max(nb1, 16), dtype=torch.uint8, device=dev)
+        sp = Cc.c_void_p(torch.cuda.current_stream().cuda_stream)
+        def dg():
+            _lib.check(L.spc_conv2d_dgrad(Cc.byref(d), Cc.c_void_p(gy.data_ptr()), Cc.c_void_p(w.data_ptr()), Cc.c_void_p(dx.data_ptr()), Cc.c_void_p(ws.data_ptr()), nb1, sp), "dgrad")
+        dg(); torch.cuda.synchronize()
+        refdx = F.conv_transpose2d(gy[:, :, :hs + R].float(), w.float(), None, 1, ((R - 1) // 2, (S - 1) // 2))[:, :, :hs]
+        e2 = (dx[:, :, :hs].float() - refdx).abs().max().item(); s2 = refdx.abs().max().item()
+        good2 = e2 <= 2e-2 * s2
+        ok &= good2
+        def fw():
+            return _ConvSpatialFn.apply(x, w, None, desc, *([None] * 9))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        res = []
+        for fn in (fw, dg):
+            fn(); torch.cuda.synchronize(); e0.record()
+            for _ in range(3): fn()
+            e1.record(); torch.cuda.synchronize(); res.append(e0.elapsed_time(e1) / 3)
+        fl = 2.0 * C * K * R * S * H * W
+        print("tap C=%d K=%d %dx%d @%dx%d fwd err %.3g/%.3g %s  dgrad err %.3g/%.3g %s | fwd %.3f ms %.0f TF/s dgrad %.3f ms %.0f TF/s" % (
+            C, K, R, S, H, W, err, scale, "OK" if good else "FAIL", e2, s2, "OK" if good2 else "FAIL", res[0], fl / res[0] / 1e9, res[1], fl / res[1] / 1e9), flush=True)
 print("ALL OK" if ok else "SOME FAILED")
