@@ -194,11 +194,22 @@ int spc_conv2d_wgrad(const spc_conv_desc* d, const void* x, const spc_halo* halo
     rc = tc_conv_wgrad(d, x, dy, dw, /*accumulate=*/1, workspace, workspace_bytes, st);
     if (rc) return rc;
     if (has_halo(halo)) {
-      // add the halo pixels' contribution: same kernel over a view that holds ONLY the strips
-      // (interior reads as zero), which is exact by linearity.
+      // add the halo pixels' contribution: the direct kernel over a view that holds ONLY the
+      // strips (interior reads as zero) -- exact by linearity -- restricted to the output strips
+      // whose windows reach outside the tile.
       p.in = make_view(nullptr, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);
-      set_error("conv_wgrad: tcgen05 + halo correction not wired yet");
-      return SPC_EUNSUPPORTED;
+      const int top = min(Ho, ceil_div(d->pad_h, d->stride_h));
+      const int bot0 = max(top, min(Ho, ceil_div(d->H + d->pad_h - d->R + 1, d->stride_h)));
+      const int left = min(Wo, ceil_div(d->pad_w, d->stride_w));
+      const int right0 = max(left, min(Wo, ceil_div(d->W + d->pad_w - d->S + 1, d->stride_w)));
+      const int rects[4][4] = {{0, 0, top, Wo}, {bot0, 0, Ho - bot0, Wo}, {top, 0, bot0 - top, left},
+                               {top, right0, bot0 - top, Wo - right0}};
+      for (int i = 0; i < 4; ++i) {
+        if (rects[i][2] <= 0 || rects[i][3] <= 0) continue;
+        p.ry0 = rects[i][0]; p.rx0 = rects[i][1]; p.rH = rects[i][2]; p.rW = rects[i][3];
+        rc = launch_wgrad_direct(p, d->dtype, st);
+        if (rc) return rc;
+      }
     }
   } else {
     p.in = make_view(x, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);

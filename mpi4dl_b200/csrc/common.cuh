@@ -102,6 +102,7 @@ struct DirectWgradParams {
   const void* dy;     // [N][K][Ho][Wo]
   float* dw;          // [K][C][R][S] fp32, accumulated with atomics (zeroed by caller)
   int K, R, S, sh, sw, ph, pw, Ho, Wo;
+  int ry0, rx0, rH, rW;   // output sub-rectangle to reduce over (rH == 0: the whole output)
 };
 int launch_wgrad_direct(const DirectWgradParams& p, int dtype, cudaStream_t st);
 int launch_bias_grad(const void* dy, float* db, int N, int K, int HW, int dtype, int accumulate, cudaStream_t st);

@@ -153,14 +153,15 @@ wgrad_direct_kernel(const DirectWgradParams p, const int kblocks, const int cblo
     const int txi = tile % tiles_x;
     const int tyi = (tile / tiles_x) % tiles_y;
     const int n = tile / (tiles_x * tiles_y);
-    const int oy0 = tyi * WG_TH, ox0 = txi * WG_TW;
+    const int oy0 = p.ry0 + tyi * WG_TH, ox0 = p.rx0 + txi * WG_TW;
+    const int oy_end = p.ry0 + p.rH, ox_end = p.rx0 + p.rW;
     __syncthreads();
     for (int i = threadIdx.x; i < WG_KB * WG_TH * WG_TW; i += WG_THREADS) {
       const int px = i % WG_TW;
       const int py = (i / WG_TW) % WG_TH;
       const int k = i / (WG_TW * WG_TH);
       float v = 0.f;
-      if (k0 + k < p.K && oy0 + py < p.Ho && ox0 + px < p.Wo)
+      if (k0 + k < p.K && oy0 + py < oy_end && ox0 + px < ox_end)
         v = to_f32<T>(dy[(((size_t)n * p.K + k0 + k) * p.Ho + oy0 + py) * p.Wo + ox0 + px]);
       dys[k * DYP + py * WG_TW + px] = v;
     }
@@ -250,13 +251,15 @@ int launch_conv_direct(const DirectConvParams& p, int dtype, cudaStream_t st) {
   return SPC_OK;
 }
 
-int launch_wgrad_direct(const DirectWgradParams& p, int dtype, cudaStream_t st) {
-  if (p.Ho <= 0 || p.Wo <= 0 || p.in.N <= 0) return SPC_OK;
+int launch_wgrad_direct(const DirectWgradParams& p_in, int dtype, cudaStream_t st) {
+  DirectWgradParams p = p_in;
+  if (p.rH == 0 && p.rW == 0) { p.ry0 = 0; p.rx0 = 0; p.rH = p.Ho; p.rW = p.Wo; }
+  if (p.rH <= 0 || p.rW <= 0 || p.in.N <= 0) return SPC_OK;
   const int PH = (WG_TH - 1) * p.sh + p.R;
   const int PW = (WG_TW - 1) * p.sw + p.S;
   const size_t smem = ((size_t)WG_KB * (WG_TH * WG_TW + 1) + (size_t)WG_CB * ((PH * PW) | 1)) * sizeof(float);
   SPC_REQUIRE(smem <= 200 * 1024, "wgrad_direct: filter %dx%d needs %zu B smem", p.R, p.S, smem);
-  const int tiles_x = ceil_div(p.Wo, WG_TW), tiles_y = ceil_div(p.Ho, WG_TH);
+  const int tiles_x = ceil_div(p.rW, WG_TW), tiles_y = ceil_div(p.rH, WG_TH);
   const int kblocks = ceil_div(p.K, WG_KB), cblocks = ceil_div(p.in.C, WG_CB);
   const int total_tiles = p.in.N * tiles_x * tiles_y;
   // enough CTAs for ~4 waves of 148 SMs x 2 resident CTAs, but at least 8 tiles each

@@ -418,27 +418,35 @@ int run_pw(const __nv_bfloat16* w, int ld, int transpose, int M, int Cin, const 
   return run_conv_tc(c, x, bias, y, ws, ws_bytes, st);
 }
 
-// ---- wgrad kernel: dW[K x C] += dY[K x P] * X[C x P]^T --------------------------------------------
+// ---- wgrad kernel: dW[K x C x taps] += dY[K x P] * shift_tap(X)[C x P]^T -------------------------
+// Both operands are K-major straight from NCHW (pixels = reduction dim, contiguous).  One work
+// item = (group of MG 128-row blocks of dY, one block of nblk input channels, a pass of TG filter
+// taps, a split of the pixel range); accumulators for all (tap, m-block) pairs of the item live in
+// TMEM ((TG*MG) x nblk columns <= 512) and are flushed with fp32 atomics.
 struct WgParams {
-  float* dw;        // [K][C] fp32 (atomic accumulation)
+  float* dw;        // [K][C][taps] fp32 (atomic accumulation)
   int K, C, P, N;
   int nblk;         // columns (input channels) per accumulator block, multiple of 16, <= 256
   int n_blocks;     // ceil(C / nblk)
   int mgroups;      // ceil(ceil(K/128) / MG)
-  int splits;       // pixel-range splits per (mgroup, nblock)
+  int splits;       // pixel-range splits per item
   int chunks_total; // N * ceil(P/64)
   int chunks_per_image;
   int stages;
+  int taps, S, ph;  // filter taps (R*S), filter width, top padding
+  int TG, passes;   // taps per pass, ceil(taps / TG)
+  int W, shiftN;    // image width; N if x is S column-shifted copies (S > 1) else 0
 };
 
 template <int MG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
-                const WgParams p) {
+                const __grid_constant__ CUtensorMap tmap_x4, const WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int b_bytes = p.nblk * 128;
-  const int stage_bytes = MG * A_BLK_BYTES + ((b_bytes + 1023) & ~1023);
+  const int b_bytes = p.nblk * 128;                        // one tap's [nblk ch][64 px] box
+  const int b_slot = (b_bytes + 1023) & ~1023;
+  const int stage_bytes = MG * A_BLK_BYTES + p.TG * b_slot;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* tfull = empty + MAX_STAGES;
@@ -457,8 +465,19 @@ pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int num_items = p.mgroups * p.n_blocks * p.splits;
+  const int num_items = p.mgroups * p.n_blocks * p.passes * p.splits;
   const int per_split = (p.chunks_total + p.splits - 1) / p.splits;
+
+  // item -> (split, tap pass, channel block, m group)
+#define WG_DECODE(it)                                                        \
+  const int sp = (it) % p.splits;                                            \
+  const int g_ = (it) / p.splits;                                            \
+  const int pass = g_ % p.passes;                                            \
+  const int nb = (g_ / p.passes) % p.n_blocks;                               \
+  const int mgp = g_ / (p.passes * p.n_blocks);                              \
+  const int tap0 = pass * p.TG;                                              \
+  const int ntap = min(p.TG, p.taps - tap0);                                 \
+  const int c_begin = sp * per_split, c_end = min(p.chunks_total, c_begin + per_split);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -466,18 +485,25 @@ pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
       tma_prefetch_desc(&tmap_x);
       int s = 0, ph = 0;
       for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
-        const int sp = it % p.splits;
-        const int g = it / p.splits;
-        const int nb = g % p.n_blocks, mgp = g / p.n_blocks;
-        const int c_begin = sp * per_split, c_end = min(p.chunks_total, c_begin + per_split);
+        WG_DECODE(it)
+        (void)mgp;
         for (int ch = c_begin; ch < c_end; ++ch) {
           const int n = ch / p.chunks_per_image, p0 = (ch % p.chunks_per_image) * 64;
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * stage_bytes;
-          mbar_arrive_expect_tx(&full[s], MG * A_BLK_BYTES + b_bytes);
+          mbar_arrive_expect_tx(&full[s], MG * A_BLK_BYTES + ntap * b_bytes);
 #pragma unroll
           for (int i = 0; i < MG; ++i) tma_load_3d(st + i * A_BLK_BYTES, &tmap_dy, &full[s], p0, (mgp * MG + i) * 128, n);
-          tma_load_3d(st + MG * A_BLK_BYTES, &tmap_x, &full[s], p0, nb * p.nblk, n);
+          if (p.taps == 1) {
+            tma_load_3d(st + MG * A_BLK_BYTES, &tmap_x, &full[s], p0, nb * p.nblk, n);
+          } else {
+            const int hq = p0 / p.W, wq = p0 - hq * p.W;
+            for (int t = 0; t < ntap; ++t) {
+              const int tap = tap0 + t;
+              tma_load_4d(st + MG * A_BLK_BYTES + t * b_slot, &tmap_x4, &full[s], wq, hq + tap / p.S - p.ph,
+                          nb * p.nblk, n + (tap % p.S) * p.shiftN);
+            }
+          }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
       }
@@ -487,8 +513,8 @@ pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
       const uint32_t idesc = umma_idesc_bf16(128, p.nblk, 0, 0);
       int s = 0, ph = 0, aph = 0;
       for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
-        const int sp = it % p.splits;
-        const int c_begin = sp * per_split, c_end = min(p.chunks_total, c_begin + per_split);
+        WG_DECODE(it)
+        (void)nb; (void)mgp;
         mbar_wait(tempty, aph ^ 1);
         tc_fence_after();
         for (int ch = c_begin; ch < c_end; ++ch) {
@@ -496,13 +522,15 @@ pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
           const uint32_t sb = sa + MG * A_BLK_BYTES;
+          for (int t = 0; t < ntap; ++t) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t bdesc = umma_desc(sb + ks * 32, 16, 1024);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t bdesc = umma_desc(sb + t * b_slot + ks * 32, 16, 1024);
 #pragma unroll
-            for (int i = 0; i < MG; ++i) {
-              const uint64_t adesc = umma_desc(sa + i * A_BLK_BYTES + ks * 32, 16, 1024);
-              umma_bf16(tmem_base + i * p.nblk, adesc, bdesc, idesc, (ch > c_begin || ks > 0) ? 1u : 0u);
+              for (int i = 0; i < MG; ++i) {
+                const uint64_t adesc = umma_desc(sa + i * A_BLK_BYTES + ks * 32, 16, 1024);
+                umma_bf16(tmem_base + (t * MG + i) * p.nblk, adesc, bdesc, idesc, (ch > c_begin || ks > 0) ? 1u : 0u);
+              }
             }
           }
           umma_commit(&empty[s]);
@@ -516,27 +544,28 @@ pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
     const int quarter = warp & 3;
     int aph = 0;
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
-      const int sp = it % p.splits;
-      const int g = it / p.splits;
-      const int nb = g % p.n_blocks, mgp = g / p.n_blocks;
-      const int c_begin = sp * per_split, c_end = min(p.chunks_total, c_begin + per_split);
+      WG_DECODE(it)
       mbar_wait(tfull, aph);
       tc_fence_after();
       if (c_end > c_begin) {
 #pragma unroll 1
-        for (int i = 0; i < MG; ++i) {
-          const int k = (mgp * MG + i) * 128 + quarter * 32 + lane;
+        for (int t = 0; t < ntap; ++t) {
 #pragma unroll 1
-          for (int cc = 0; cc * 32 < p.nblk; ++cc) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + i * p.nblk + cc * 32, r);
-            tmem_ld_wait();
-            if (k < p.K) {
+          for (int i = 0; i < MG; ++i) {
+            const int k = (mgp * MG + i) * 128 + quarter * 32 + lane;
+#pragma unroll 1
+            for (int cc = 0; cc * 32 < p.nblk; ++cc) {
+              uint32_t r[32];
+              tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (t * MG + i) * p.nblk + cc * 32, r);
+              tmem_ld_wait();
+              if (k < p.K) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int cl = cc * 32 + j;
-                const int c = nb * p.nblk + cl;
-                if (cl < p.nblk && c < p.C) atomicAdd(&p.dw[(size_t)k * p.C + c], __uint_as_float(r[j]));
+                for (int j = 0; j < 32; ++j) {
+                  const int cl = cc * 32 + j;
+                  const int c = nb * p.nblk + cl;
+                  if (cl < p.nblk && c < p.C)
+                    atomicAdd(&p.dw[((size_t)k * p.C + c) * p.taps + tap0 + t], __uint_as_float(r[j]));
+                }
               }
             }
           }
@@ -547,55 +576,77 @@ pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
       aph ^= 1;
     }
   }
+#undef WG_DECODE
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 template <int MG>
-int launch_wg(const CUtensorMap& tdy, const CUtensorMap& tx, WgParams p, cudaStream_t st) {
-  const int stage_bytes = MG * A_BLK_BYTES + ((p.nblk * 128 + 1023) & ~1023);
+int launch_wg(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMap& tx4, WgParams p, cudaStream_t st) {
+  const int b_slot = (p.nblk * 128 + 1023) & ~1023;
+  // taps per pass: TMEM columns and a stage small enough for >= 2 pipeline stages
+  int TG = 512 / (MG * p.nblk);
+  if (TG > p.taps) TG = p.taps;
+  while (TG > 1 && MG * A_BLK_BYTES + TG * b_slot > (SMEM_LIMIT - SMEM_AUX) / 2) --TG;
+  p.TG = TG;
+  p.passes = (p.taps + TG - 1) / TG;
+  const int stage_bytes = MG * A_BLK_BYTES + TG * b_slot;
   p.stages = (SMEM_LIMIT - SMEM_AUX) / stage_bytes;
   if (p.stages > 6) p.stages = 6;
   SPC_REQUIRE(p.stages >= 2, "tcgen05 wgrad: smem budget");
+  const int groups = p.mgroups * p.n_blocks * p.passes;
+  int splits = (2 * 148 + groups - 1) / groups;
+  if (splits > p.chunks_total / 8) splits = p.chunks_total / 8;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
   const int smem = p.stages * stage_bytes + SMEM_AUX;
   auto kern = pw_wgrad_kernel<MG>;
   SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int items = p.mgroups * p.n_blocks * p.splits;
-  kern<<<items < sms ? items : sms, TC_THREADS, smem, st>>>(tdy, tx, p);
+  const int items = groups * p.splits;
+  kern<<<items < sms ? items : sms, TC_THREADS, smem, st>>>(tdy, tx, tx4, p);
   count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
 }
 
-int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K, int C, int N, int P, cudaStream_t st) {
+// x: activations [N][C][H][W] (taps == 1) or the S column-shifted copies [S][N][C][H][W]
+int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K, int C, int N, int H, int W, int R,
+              int S, int ph, cudaStream_t st) {
+  const int P = H * W;
   WgParams p{};
   p.dw = dw; p.K = K; p.C = C; p.P = P; p.N = N;
+  p.taps = R * S; p.S = S; p.ph = ph; p.W = W; p.shiftN = S > 1 ? N : 0;
   p.n_blocks = (C + 255) / 256;
   p.nblk = round_up((C + p.n_blocks - 1) / p.n_blocks, 16);
   const int MBtot = (K + 127) / 128;
-  int MG = 512 / p.nblk;
+  int MG = p.taps > 1 ? 1 : 512 / p.nblk;
   if (MG > MBtot) MG = MBtot;
   MG = MG >= 4 ? 4 : (MG >= 2 ? 2 : 1);
   p.mgroups = (MBtot + MG - 1) / MG;
   p.chunks_per_image = (P + 63) / 64;
   p.chunks_total = p.chunks_per_image * N;
-  const int groups = p.mgroups * p.n_blocks;
-  int splits = (2 * 148 + groups - 1) / groups;
-  if (splits > p.chunks_total / 8) splits = p.chunks_total / 8;
-  if (splits < 1) splits = 1;
-  p.splits = splits;
-  CUtensorMap tdy, tx;
+  CUtensorMap tdy, tx, tx4;
   int rc = make_act_tmap(&tdy, dy, P, K, N, 128);
   if (rc) return rc;
-  rc = make_act_tmap(&tx, x, P, C, N, p.nblk);
-  if (rc) return rc;
-  if (MG == 1) return launch_wg<1>(tdy, tx, p, st);
-  if (MG == 2) return launch_wg<2>(tdy, tx, p, st);
-  return launch_wg<4>(tdy, tx, p, st);
+  if (p.taps > 1) {
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)N * S};
+    const uint64_t strides[4] = {0, (uint64_t)W * 2, (uint64_t)P * 2, (uint64_t)P * C * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)p.nblk, 1};
+    rc = make_tmap(&tx4, x, 4, dims, strides, box);
+    if (rc) return rc;
+    tx = tx4;
+  } else {
+    rc = make_act_tmap(&tx, x, P, C, N, p.nblk);
+    if (rc) return rc;
+    tx4 = tx;
+  }
+  if (MG == 1) return launch_wg<1>(tdy, tx, tx4, p, st);
+  if (MG == 2) return launch_wg<2>(tdy, tx, tx4, p, st);
+  return launch_wg<4>(tdy, tx, tx4, p, st);
 }
 
 // ---- stride-2 pointwise convs: subsample / zero-upsample passes around the GEMM ------------------
@@ -715,7 +766,7 @@ bool pw_shape_ok(const spc_conv_desc* d) {
 
 bool tc_supported(const spc_conv_desc* d, int op) {
   if (pw_shape_ok(d)) return true;
-  if (tap_shape_ok(d)) return op != 2;   // multi-tap wgrad: next
+  if (tap_shape_ok(d)) return true;
   return false;
 }
 
@@ -728,8 +779,8 @@ static size_t wbytes(const spc_conv_desc* d, int op) {
 }
 size_t tc_workspace_bytes(const spc_conv_desc* d, int op) {
   size_t b = wbytes(d, op);
-  if (d->S > 1 && op < 2)   // S column-shifted copies of the conv input (x for fprop, dy for dgrad)
-    b += align1k((size_t)d->S * d->N * (op == 0 ? d->C : d->K) * d->H * d->W * 2) + 2048;
+  if (d->S > 1)   // S column-shifted copies of the conv input (x for fprop / wgrad, dy for dgrad)
+    b += align1k((size_t)d->S * d->N * (op == 1 ? d->K : d->C) * d->H * d->W * 2) + 2048;
   if (is_s2(d)) b += align1k((size_t)d->N * d->C * (d->H / 2) * (d->W / 2) * 2) + 1024;
   return b + 1024;
 }
@@ -789,16 +840,27 @@ int tc_conv_wgrad(const spc_conv_desc* d, const void* x, const void* dy, float* 
                   size_t ws_bytes, cudaStream_t st) {
   // the kernel accumulates with atomics; api.cu has already zeroed dw when !accumulate
   (void)accumulate;
+  const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+  if (d->R * d->S > 1) {
+    if (d->S > 1) {
+      SPC_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(d, 2), "tcgen05 wgrad: workspace too small");
+      void* xs = reinterpret_cast<void*>(align1k(reinterpret_cast<uintptr_t>(ws)));
+      int rc = launch_shift_copies(x, xs, (size_t)d->N * d->C, d->H, d->W, d->S, d->pad_w, st);
+      if (rc) return rc;
+      xb = reinterpret_cast<const __nv_bfloat16*>(xs);
+    }
+    return run_wgrad(xb, dyb, dw, d->K, d->C, d->N, d->H, d->W, d->R, d->S, d->pad_h, st);
+  }
   if (is_s2(d)) {
     SPC_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(d, 2), "tcgen05 wgrad: workspace too small");
     void* xs = reinterpret_cast<void*>(align1k(reinterpret_cast<uintptr_t>(ws)));
     int rc = launch_resample(false, x, xs, (size_t)d->N * d->C, d->H, d->W, st);
     if (rc) return rc;
-    return run_wgrad(reinterpret_cast<const __nv_bfloat16*>(xs), reinterpret_cast<const __nv_bfloat16*>(dy), dw, d->K,
-                     d->C, d->N, (d->H / 2) * (d->W / 2), st);
+    return run_wgrad(reinterpret_cast<const __nv_bfloat16*>(xs), dyb, dw, d->K, d->C, d->N, d->H / 2, d->W / 2, 1, 1, 0,
+                     st);
   }
-  return run_wgrad(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), dw, d->K,
-                   d->C, d->N, d->H * d->W, st);
+  return run_wgrad(xb, dyb, dw, d->K, d->C, d->N, 1, d->H * d->W, 1, 1, 0, st);
 }
 
 }  // namespace spc

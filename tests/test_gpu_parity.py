@@ -266,7 +266,12 @@ def test_full_size_properties_linearity_and_tile_equals_slice():
     strips = [None] * 9
     strips[5] = full[:, :, :, W:W + 1].contiguous()
     y_left = conv(left, strips)
-    assert torch.equal(y_left, y_full[:, :, :, :W])
+    # interior columns come from the same (tcgen05) kernel in both runs: bit-exact.  The last
+    # column is recomputed by the boundary kernel from the halo strip (different fp32 summation
+    # order), so it may differ by one bf16 rounding step.
+    assert torch.equal(y_left[..., :W - 1], y_full[..., :W - 1])
+    edge, ref_edge = y_left[..., W - 1].float(), y_full[..., W - 1].float()
+    assert torch.allclose(edge, ref_edge, rtol=1e-2, atol=1e-2)
     # avg-pool checksum on the same tensor
     N, Cc, h, ww = left.shape
     yp = _PoolFn.apply(left, (N, Cc, h, ww, 3, 1, 1, _lib.SPC_POOL_AVG, code), *([None] * 9))
