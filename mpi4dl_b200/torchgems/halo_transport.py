@@ -107,7 +107,9 @@ class PeerTransport:
         self.arena = torch.as_tensor(_CudaMem(self.base, self.arena_bytes), device=device)
         handle = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
         _lib.check(L.spc_mailbox_export(mb, handle), "spc_mailbox_export")
-        self.handle = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(device)
+        # the 64-byte IPC handle travels through torch.distributed once per neighbour
+        self.hdev = device if (dist.is_initialized() and dist.get_backend() == "nccl") else torch.device("cpu")
+        self.handle = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(self.hdev)
         self.peers = {}       # rank -> (mailbox ptr, data base ptr)
         self.data_top = 0
         self.flag_top = 0
@@ -115,7 +117,7 @@ class PeerTransport:
     def _peer(self, rank):
         if rank not in self.peers:
             L = _lib.lib()
-            theirs = torch.empty(_lib.IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
+            theirs = torch.empty(_lib.IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.hdev)
             reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, self.handle, rank),
                                            dist.P2POp(dist.irecv, theirs, rank)])
             for r in reqs:
