@@ -108,7 +108,8 @@ struct PwParams {
   int out_bufs;                // 1 or 2 epilogue staging buffers
   int taps, S, ph, pw;         // filter taps (R*S), filter width, zero padding (tap mode)
   int W, Mpad;                 // image width (tap mode: tiles are 64-pixel row segments), padded M
-  int shiftN;                  // N when the activations are S column-shifted copies (S > 1), else 0
+  int shiftN;                  // N when the activations are S column-shifted copies, else 0
+  int rowmul;                  // input row = rowmul * output row + tap row offset (2 for stride-2 convs)
   const __nv_bfloat16* bias;   // [M] or null
 };
 
@@ -191,7 +192,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
               const int q = p0 + j * 64, hq = q / p.W, wq = q - hq * p.W;
-              tma_load_4d(st + j * B_BLK_BYTES, &tmap_x4, &full[s], wq, hq + dr, kc * BK, img);
+              tma_load_4d(st + j * B_BLK_BYTES, &tmap_x4, &full[s], wq, hq * p.rowmul + dr, kc * BK, img);
             }
           }
           if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -334,7 +335,7 @@ int make_act_tmap(CUtensorMap* m, const void* base, int P, int Cc, int N, int bo
   return make_tmap(m, base, 3, dims, strides, box);
 }
 
-int launch_shift_copies(const void* x, void* xs, size_t planes, int H, int W, int S, int pw, cudaStream_t st);
+int launch_shift_copies(const void* x, void* xs, size_t planes, int H, int W, int S, int pw, int cs, cudaStream_t st);
 
 // Geometry of one tcgen05 convolution launch (fprop, or dgrad expressed as a convolution of dY).
 struct TcConv {
@@ -343,36 +344,44 @@ struct TcConv {
   int flip;                    // rotate taps by 180 degrees (dgrad)
   int M, Cin;                  // output channels, reduction channels
   int R, S, ph, pw;            // filter and zero padding
-  int H, W, N;                 // image (stride 1: output extent == input extent)
+  int H, W, N;                 // input image
+  int stride;                  // 1 or 2 (both axes)
+  const __nv_bfloat16* prepacked;   // if set: weights already in [taps][Mpad][Cpad] layout (1024-aligned)
 };
 
 // Y[N][M][H*W] = sum_taps Wp[tap][M x Cin] * shift_tap(X[N][Cin][H][W])  (+bias)
 int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bias, __nv_bfloat16* y, void* ws,
                 size_t ws_bytes, cudaStream_t st) {
   const int taps = c.R * c.S;
-  const int P = c.H * c.W;
+  const int cs = c.stride;
+  const int Ho = c.H / cs, Wo = c.W / cs;
+  const int Pin = c.H * c.W, P = Ho * Wo;            // P: output pixels per image
   const int Mpad = round_up(c.M, 128), Cpad = round_up(c.Cin, BK);
+  const bool copies = (c.S > 1 || cs > 1) && taps > 1;   // column-shifted (and subsampled) copies of the input
   const uintptr_t ws0 = reinterpret_cast<uintptr_t>(ws);
   const uintptr_t wp_addr = (ws0 + 1023) & ~(uintptr_t)1023;
-  const uintptr_t xs_addr = (wp_addr + (size_t)taps * Mpad * Cpad * 2 + 1023) & ~(uintptr_t)1023;
-  const size_t xs_bytes = c.S > 1 ? (size_t)c.S * c.N * c.Cin * P * 2 : 0;
+  const size_t wp_bytes = c.prepacked ? 0 : (size_t)taps * Mpad * Cpad * 2;
+  const uintptr_t xs_addr = (wp_addr + wp_bytes + 1023) & ~(uintptr_t)1023;
+  const size_t xs_bytes = copies ? (size_t)c.S * c.N * c.Cin * c.H * Wo * 2 : 0;
   const size_t need = (xs_addr - ws0) + xs_bytes;
-  SPC_REQUIRE(ws && ws_bytes >= need, "tcgen05 conv: workspace too small (%zu < %zu)", ws_bytes, need);
-  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(wp_addr);
-  const __nv_bfloat16* xsrc = x;
-  if (c.S > 1) {
-    void* xs = reinterpret_cast<void*>(xs_addr);
-    int rc0 = launch_shift_copies(x, xs, (size_t)c.N * c.Cin, c.H, c.W, c.S, c.pw, st);
-    if (rc0) return rc0;
-    xsrc = reinterpret_cast<const __nv_bfloat16*>(xs);
-  }
-  {
+  SPC_REQUIRE((ws && ws_bytes >= need) || need <= 1024, "tcgen05 conv: workspace too small (%zu < %zu)", ws_bytes, need);
+  const __nv_bfloat16* wp = c.prepacked;
+  if (!c.prepacked) {
+    __nv_bfloat16* wpm = reinterpret_cast<__nv_bfloat16*>(wp_addr);
     const int total = taps * Mpad * Cpad;
     int blocks = (total + 255) / 256;
     if (blocks > 1184) blocks = 1184;
-    repack_weights_kernel<<<blocks, 256, 0, st>>>(c.w, wp, c.M, c.Cin, Mpad, Cpad, taps, c.sm, c.sc, c.flip);
+    repack_weights_kernel<<<blocks, 256, 0, st>>>(c.w, wpm, c.M, c.Cin, Mpad, Cpad, taps, c.sm, c.sc, c.flip);
     count_launch();
     SPC_CHECK_CUDA(cudaGetLastError());
+    wp = wpm;
+  }
+  const __nv_bfloat16* xsrc = x;
+  if (copies) {
+    void* xs = reinterpret_cast<void*>(xs_addr);
+    int rc0 = launch_shift_copies(x, xs, (size_t)c.N * c.Cin, c.H, c.W, c.S, c.pw, cs, st);
+    if (rc0) return rc0;
+    xsrc = reinterpret_cast<const __nv_bfloat16*>(xs);
   }
   CUtensorMap tw, tx, tx4, ty;
   {
@@ -382,23 +391,27 @@ int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bi
     int rc = make_tmap(&tw, wp, 2, dims, strides, box);
     if (rc) return rc;
   }
-  int rc = make_act_tmap(&tx, x, P, c.Cin, c.N, BK);
-  if (rc) return rc;
+  int rc;
   if (taps > 1) {
-    const uint64_t dims[4] = {(uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.Cin, (uint64_t)c.N * c.S};
-    const uint64_t strides[4] = {0, (uint64_t)c.W * 2, (uint64_t)P * 2, (uint64_t)P * c.Cin * 2};
+    // (copies of) the input as [img][Cin][H][Wo]; img = n + s*N for the copy of filter column s
+    const uint64_t dims[4] = {(uint64_t)Wo, (uint64_t)c.H, (uint64_t)c.Cin, (uint64_t)c.N * (copies ? c.S : 1)};
+    const uint64_t strides[4] = {0, (uint64_t)Wo * 2, (uint64_t)c.H * Wo * 2, (uint64_t)c.H * Wo * c.Cin * 2};
     const uint32_t box[4] = {64, 1, BK, 1};
     rc = make_tmap(&tx4, xsrc, 4, dims, strides, box);
     if (rc) return rc;
+    tx = tx4;
   } else {
+    rc = make_act_tmap(&tx, x, Pin, c.Cin, c.N, BK);
+    if (rc) return rc;
     tx4 = tx;
   }
   rc = make_act_tmap(&ty, y, P, c.M, c.N, 128);
   if (rc) return rc;
   PwParams p{};
   p.bias = bias; p.M = c.M; p.Cin = c.Cin; p.P = P; p.N = c.N;
-  p.taps = taps; p.S = c.S; p.ph = c.ph; p.pw = c.pw; p.W = c.W; p.Mpad = Mpad;
-  p.shiftN = c.S > 1 ? c.N : 0;
+  p.taps = taps; p.S = c.S; p.ph = c.ph; p.pw = c.pw; p.W = Wo; p.Mpad = Mpad;
+  p.shiftN = copies ? c.N : 0;
+  p.rowmul = cs;
   const int MBtot = Mpad / 128;
   p.num_mg = (Mpad + 511) / 512;
   p.tiles_per_image = (P + BN - 1) / BN;
@@ -414,7 +427,7 @@ int run_pw(const __nv_bfloat16* w, int ld, int transpose, int M, int Cin, const 
   TcConv c{};
   c.w = w;
   c.sm = transpose ? 1 : ld; c.sc = transpose ? ld : 1; c.flip = 0;
-  c.M = M; c.Cin = Cin; c.R = 1; c.S = 1; c.ph = 0; c.pw = 0; c.H = 1; c.W = P; c.N = N;
+  c.M = M; c.Cin = Cin; c.R = 1; c.S = 1; c.ph = 0; c.pw = 0; c.H = 1; c.W = P; c.N = N; c.stride = 1;
   return run_conv_tc(c, x, bias, y, ws, ws_bytes, st);
 }
 
@@ -435,7 +448,8 @@ struct WgParams {
   int stages;
   int taps, S, ph;  // filter taps (R*S), filter width, top padding
   int TG, passes;   // taps per pass, ceil(taps / TG)
-  int W, shiftN;    // image width; N if x is S column-shifted copies (S > 1) else 0
+  int W, shiftN;    // OUTPUT image width; N if x is the S column-shifted copies, else 0
+  int rowmul;       // input row = rowmul * output row + tap row offset
 };
 
 template <int MG>
@@ -500,7 +514,7 @@ pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
             const int hq = p0 / p.W, wq = p0 - hq * p.W;
             for (int t = 0; t < ntap; ++t) {
               const int tap = tap0 + t;
-              tma_load_4d(st + MG * A_BLK_BYTES + t * b_slot, &tmap_x4, &full[s], wq, hq + tap / p.S - p.ph,
+              tma_load_4d(st + MG * A_BLK_BYTES + t * b_slot, &tmap_x4, &full[s], wq, hq * p.rowmul + tap / p.S - p.ph,
                           nb * p.nblk, n + (tap % p.S) * p.shiftN);
             }
           }
@@ -613,13 +627,14 @@ int launch_wg(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMap& 
   return SPC_OK;
 }
 
-// x: activations [N][C][H][W] (taps == 1) or the S column-shifted copies [S][N][C][H][W]
-int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K, int C, int N, int H, int W, int R,
-              int S, int ph, cudaStream_t st) {
-  const int P = H * W;
+// x: activations [N][C][Hin][Wo] (taps == 1: Hin == Ho) or their S column-shifted (and, for
+// stride 2, column-subsampled) copies [S][N][C][Hin][Wo].  Ho x Wo = extent of dy.
+int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K, int C, int N, int Ho, int Wo, int Hin,
+              int R, int S, int ph, int stride, bool copies, cudaStream_t st) {
+  const int P = Ho * Wo;
   WgParams p{};
   p.dw = dw; p.K = K; p.C = C; p.P = P; p.N = N;
-  p.taps = R * S; p.S = S; p.ph = ph; p.W = W; p.shiftN = S > 1 ? N : 0;
+  p.taps = R * S; p.S = S; p.ph = ph; p.W = Wo; p.shiftN = copies ? N : 0; p.rowmul = stride;
   p.n_blocks = (C + 255) / 256;
   p.nblk = round_up((C + p.n_blocks - 1) / p.n_blocks, 16);
   const int MBtot = (K + 127) / 128;
@@ -633,8 +648,8 @@ int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K,
   int rc = make_act_tmap(&tdy, dy, P, K, N, 128);
   if (rc) return rc;
   if (p.taps > 1) {
-    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)N * S};
-    const uint64_t strides[4] = {0, (uint64_t)W * 2, (uint64_t)P * 2, (uint64_t)P * C * 2};
+    const uint64_t dims[4] = {(uint64_t)Wo, (uint64_t)Hin, (uint64_t)C, (uint64_t)N * (copies ? S : 1)};
+    const uint64_t strides[4] = {0, (uint64_t)Wo * 2, (uint64_t)Hin * Wo * 2, (uint64_t)Hin * Wo * C * 2};
     const uint32_t box[4] = {64, 1, (uint32_t)p.nblk, 1};
     rc = make_tmap(&tx4, x, 4, dims, strides, box);
     if (rc) return rc;
@@ -647,6 +662,55 @@ int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K,
   if (MG == 1) return launch_wg<1>(tdy, tx, tx4, p, st);
   if (MG == 2) return launch_wg<2>(tdy, tx, tx4, p, st);
   return launch_wg<4>(tdy, tx, tx4, p, st);
+}
+
+// ---- 3x3 stride-2 dgrad: the four output-parity classes of dX as channel groups of ONE 2x2-tap
+// convolution over dY, then an interleave ("depth to space") pass.
+//   dx[c, 2i+a, 2j+b] = sum_{u,v in {0,1}} sum_k Wq[(u,v)][(a,b)*C + c][k] * dy[k, i+u, j+v]
+//   with Wq = w[k][c][r(a,u)][s(b,v)],  r(0,0)=1, r(1,0)=2, r(1,1)=0, r(0,1)=none (zero).
+__global__ void repack_dgrad_s2_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wp, int K,
+                                       int C, int Mpad, int Kpad) {
+  const int total = 4 * Mpad * Kpad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % Kpad;
+    const int m = (i / Kpad) % Mpad;
+    const int tap = i / (Kpad * Mpad);
+    const int u = tap >> 1, v = tap & 1;
+    __nv_bfloat16 val = __float2bfloat16(0.f);
+    if (m < 4 * C && k < K) {
+      const int cls = m / C, c = m % C;
+      const int a = cls >> 1, b = cls & 1;
+      const int r = a == 0 ? (u == 0 ? 1 : -1) : (u == 0 ? 2 : 0);
+      const int sx = b == 0 ? (v == 0 ? 1 : -1) : (v == 0 ? 2 : 0);
+      if (r >= 0 && sx >= 0) val = w[(((size_t)k * C + c) * 3 + r) * 3 + sx];
+    }
+    wp[i] = val;
+  }
+}
+// dx[n][c][2i+a][2j+b] = t[n][(2a+b)*C + c][i][j]; 8 input pixels of both column classes per thread
+__global__ void interleave_s2_kernel(const __nv_bfloat16* __restrict__ t, __nv_bfloat16* __restrict__ dx, int N, int C,
+                                     int Ho, int Wo) {
+  const int wv = Wo / 8;
+  const size_t total = (size_t)N * C * 2 * Ho * wv;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % wv);
+    const int oy = (int)((i / wv) % Ho);
+    const int a = (int)((i / ((size_t)wv * Ho)) % 2);
+    const size_t nc = i / ((size_t)wv * Ho * 2);
+    const int c = (int)(nc % C);
+    const size_t n = nc / C;
+    const size_t plane = (size_t)Ho * Wo;
+    const __nv_bfloat16* t0 = t + ((n * 4 + 2 * a) * C + c) * plane + (size_t)oy * Wo + v * 8;   // b = 0
+    const uint4 e = __ldg(reinterpret_cast<const uint4*>(t0));
+    const uint4 o = __ldg(reinterpret_cast<const uint4*>(t0 + (size_t)C * plane));               // b = 1
+    uint4 lo, hi;
+    lo.x = __byte_perm(e.x, o.x, 0x5410); lo.y = __byte_perm(e.x, o.x, 0x7632);
+    lo.z = __byte_perm(e.y, o.y, 0x5410); lo.w = __byte_perm(e.y, o.y, 0x7632);
+    hi.x = __byte_perm(e.z, o.z, 0x5410); hi.y = __byte_perm(e.z, o.z, 0x7632);
+    hi.z = __byte_perm(e.w, o.w, 0x5410); hi.w = __byte_perm(e.w, o.w, 0x7632);
+    uint4* d = reinterpret_cast<uint4*>(dx + ((nc * 2 * Ho) + 2 * oy + a) * (size_t)(2 * Wo) + v * 16);
+    d[0] = lo; d[1] = hi;
+  }
 }
 
 // ---- stride-2 pointwise convs: subsample / zero-upsample passes around the GEMM ------------------
@@ -705,9 +769,12 @@ int launch_resample(bool up, const void* src, void* dst, size_t planes, int H, i
 // horizontal taps of an R x S filter cannot be fetched as shifted boxes.  For S > 1 one pre-pass
 // writes the S column-shifted, zero-filled copies  xs[s][plane][h][w] = x[plane][h][w + s - pw];
 // every tap (r, s) is then an ALIGNED box of copy s at row offset r - ph.
+// With column stride cs (stride-2 convs) the copies are also subsampled:
+//     xs[s][plane][h][j] = x[plane][h][cs*j + s - pw],  j < W/cs.
 __global__ void shift_copies_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xs,
-                                    size_t planes, int H, int W, int S, int pw) {
-  const int wv = W / 8;
+                                    size_t planes, int H, int W, int S, int pw, int cs) {
+  const int Wv = W / cs;
+  const int wv = Wv / 8;
   const size_t rows = planes * H;
   const size_t total = rows * wv * S;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -715,21 +782,21 @@ __global__ void shift_copies_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
     const size_t row = (i / wv) % rows;
     const int sidx = (int)(i / ((size_t)wv * rows));
     const __nv_bfloat16* src = x + row * W;
-    const int w0 = v * 8 + sidx - pw;
+    const int w0 = v * 8 * cs + sidx - pw;
     __nv_bfloat16 e[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int w = w0 + j;
+      const int w = w0 + j * cs;
       e[j] = ((unsigned)w < (unsigned)W) ? src[w] : __float2bfloat16(0.f);
     }
-    *reinterpret_cast<uint4*>(xs + ((size_t)sidx * rows + row) * W + v * 8) = *reinterpret_cast<const uint4*>(e);
+    *reinterpret_cast<uint4*>(xs + ((size_t)sidx * rows + row) * Wv + v * 8) = *reinterpret_cast<const uint4*>(e);
   }
 }
-int launch_shift_copies(const void* x, void* xs, size_t planes, int H, int W, int S, int pw, cudaStream_t st) {
-  const size_t total = planes * H * (W / 8) * S;
+int launch_shift_copies(const void* x, void* xs, size_t planes, int H, int W, int S, int pw, int cs, cudaStream_t st) {
+  const size_t total = planes * H * (W / cs / 8) * S;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  shift_copies_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)xs, planes, H, W, S, pw);
+  shift_copies_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)xs, planes, H, W, S, pw, cs);
   count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
@@ -738,13 +805,16 @@ int launch_shift_copies(const void* x, void* xs, size_t planes, int H, int W, in
 inline bool is_s2(const spc_conv_desc* d) { return d->stride_h == 2 && d->stride_w == 2; }
 inline size_t align1k(size_t b) { return (b + 1023) & ~(size_t)1023; }
 
-bool tap_shape_ok(const spc_conv_desc* d) {   // RxS stride-1 "same" convs on 64-pixel row segments
+bool tap_shape_ok(const spc_conv_desc* d) {   // odd RxS "same" convs, stride 1 or 2, on 64-pixel output row segments
   if (d->dtype != SPC_BF16) return false;
   if (d->R * d->S == 1 || d->R * d->S > 49) return false;
-  if (d->stride_h != 1 || d->stride_w != 1) return false;
-  if (d->W % 64 != 0) return false;
-  if ((size_t)d->S * d->N * (d->C > d->K ? d->C : d->K) * d->H * d->W * 2 > (8ull << 30)) return false;
   if ((d->R & 1) == 0 || (d->S & 1) == 0) return false;
+  const bool s1 = d->stride_h == 1 && d->stride_w == 1, s2 = d->stride_h == 2 && d->stride_w == 2;
+  if (!s1 && !s2) return false;
+  if (s2 && (d->H % 2 || d->W % 2)) return false;
+  const int Wo = d->W / d->stride_w;
+  if (Wo % 64 != 0) return false;
+  if ((size_t)d->S * d->N * (d->C > d->K ? d->C : d->K) * d->H * Wo * 2 > (8ull << 30)) return false;
   return (long long)d->H * d->W < (1ll << 31);
 }
 
@@ -766,7 +836,10 @@ bool pw_shape_ok(const spc_conv_desc* d) {
 
 bool tc_supported(const spc_conv_desc* d, int op) {
   if (pw_shape_ok(d)) return true;
-  if (tap_shape_ok(d)) return true;
+  if (tap_shape_ok(d)) {
+    if (op == 1 && is_s2(d)) return d->R == 3 && d->S == 3 && 4 * d->C <= 2048;   // parity-class dgrad
+    return true;
+  }
   return false;
 }
 
@@ -778,11 +851,23 @@ static size_t wbytes(const spc_conv_desc* d, int op) {
   return 0;
 }
 size_t tc_workspace_bytes(const spc_conv_desc* d, int op) {
-  size_t b = wbytes(d, op);
-  if (d->S > 1)   // S column-shifted copies of the conv input (x for fprop / wgrad, dy for dgrad)
-    b += align1k((size_t)d->S * d->N * (op == 1 ? d->K : d->C) * d->H * d->W * 2) + 2048;
-  if (is_s2(d)) b += align1k((size_t)d->N * d->C * (d->H / 2) * (d->W / 2) * 2) + 1024;
-  return b + 1024;
+  const size_t taps = (size_t)d->R * d->S;
+  const int cs = d->stride_w;
+  size_t b = wbytes(d, op) + 4096;
+  if (taps == 1) {
+    if (is_s2(d)) b += align1k((size_t)d->N * d->C * (d->H / 2) * (d->W / 2) * 2) + 1024;
+    return b;
+  }
+  const size_t Ho = d->H / cs, Wo = d->W / cs;
+  if (op == 1 && is_s2(d)) {
+    // Wq[4][4C pad][K pad] + 2 column-shifted copies of dy + the 4-class output planes
+    b = align1k(4ull * round_up(4 * d->C, 128) * round_up(d->K, BK) * 2) + 4096;
+    b += align1k(2ull * d->N * d->K * Ho * Wo * 2) + align1k(4ull * d->N * d->C * Ho * Wo * 2) + 4096;
+    return b;
+  }
+  if (d->S > 1 || cs > 1)   // S column-shifted (stride 2: also subsampled) copies of the conv input
+    b += align1k((size_t)d->S * d->N * (op == 1 ? d->K : d->C) * d->H * Wo * 2) + 2048;
+  return b;
 }
 
 int tc_conv_fwd(const spc_conv_desc* d, const void* x, const void* w, const void* bias, void* y, void* ws,
@@ -793,7 +878,7 @@ int tc_conv_fwd(const spc_conv_desc* d, const void* x, const void* w, const void
     c.w = reinterpret_cast<const __nv_bfloat16*>(w);
     c.sm = (long long)d->C * d->R * d->S; c.sc = (long long)d->R * d->S; c.flip = 0;
     c.M = d->K; c.Cin = d->C; c.R = d->R; c.S = d->S; c.ph = d->pad_h; c.pw = d->pad_w;
-    c.H = d->H; c.W = d->W; c.N = d->N;
+    c.H = d->H; c.W = d->W; c.N = d->N; c.stride = d->stride_h;
     return run_conv_tc(c, reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(bias),
                        reinterpret_cast<__nv_bfloat16*>(y), ws, ws_bytes, st);
   }
@@ -814,12 +899,42 @@ int tc_conv_dgrad(const spc_conv_desc* d, const void* dy, const void* w, void* d
                   cudaStream_t st) {
   // dX[C x P] = W^T[C x K] * dY[K x P]
   SPC_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(d, 1), "tcgen05 conv: workspace too small");
+  if (d->R * d->S > 1 && is_s2(d)) {   // 3x3 stride 2: four parity classes as channel groups, then interleave
+    const int Ho = d->H / 2, Wo = d->W / 2;
+    const int Mq = 4 * d->C, Mpad = round_up(Mq, 128), Kpad = round_up(d->K, BK);
+    uintptr_t a = align1k(reinterpret_cast<uintptr_t>(ws));
+    __nv_bfloat16* wq = reinterpret_cast<__nv_bfloat16*>(a);
+    a = align1k(a + (size_t)4 * Mpad * Kpad * 2);
+    __nv_bfloat16* tmp = reinterpret_cast<__nv_bfloat16*>(a);
+    a = align1k(a + (size_t)4 * d->N * d->C * Ho * Wo * 2);
+    {
+      const int total = 4 * Mpad * Kpad;
+      int blocks = (total + 255) / 256;
+      if (blocks > 1184) blocks = 1184;
+      repack_dgrad_s2_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(w), wq, d->K, d->C, Mpad, Kpad);
+      count_launch();
+      SPC_CHECK_CUDA(cudaGetLastError());
+    }
+    TcConv c{};
+    c.prepacked = wq;
+    c.M = Mq; c.Cin = d->K; c.R = 2; c.S = 2; c.ph = 0; c.pw = 0; c.H = Ho; c.W = Wo; c.N = d->N; c.stride = 1;
+    int rc = run_conv_tc(c, reinterpret_cast<const __nv_bfloat16*>(dy), nullptr, tmp, reinterpret_cast<void*>(a),
+                         ws_bytes - (a - reinterpret_cast<uintptr_t>(ws)), st);
+    if (rc) return rc;
+    const size_t total = (size_t)d->N * d->C * 2 * Ho * (Wo / 8);
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    interleave_s2_kernel<<<(int)blocks, 256, 0, st>>>(tmp, reinterpret_cast<__nv_bfloat16*>(dx), d->N, d->C, Ho, Wo);
+    count_launch();
+    SPC_CHECK_CUDA(cudaGetLastError());
+    return SPC_OK;
+  }
   if (d->R * d->S > 1) {   // stride-1 dgrad = correlation of dY with the transposed, 180-degree rotated filter
     TcConv c{};
     c.w = reinterpret_cast<const __nv_bfloat16*>(w);
     c.sm = (long long)d->R * d->S; c.sc = (long long)d->C * d->R * d->S; c.flip = 1;
     c.M = d->C; c.Cin = d->K; c.R = d->R; c.S = d->S; c.ph = d->R - 1 - d->pad_h; c.pw = d->S - 1 - d->pad_w;
-    c.H = d->H; c.W = d->W; c.N = d->N;
+    c.H = d->H; c.W = d->W; c.N = d->N; c.stride = 1;
     return run_conv_tc(c, reinterpret_cast<const __nv_bfloat16*>(dy), nullptr, reinterpret_cast<__nv_bfloat16*>(dx), ws,
                        ws_bytes, st);
   }
@@ -843,24 +958,26 @@ int tc_conv_wgrad(const spc_conv_desc* d, const void* x, const void* dy, float* 
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
   if (d->R * d->S > 1) {
-    if (d->S > 1) {
+    const int cs = d->stride_h;
+    const bool copies = d->S > 1 || cs > 1;
+    if (copies) {
       SPC_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(d, 2), "tcgen05 wgrad: workspace too small");
       void* xs = reinterpret_cast<void*>(align1k(reinterpret_cast<uintptr_t>(ws)));
-      int rc = launch_shift_copies(x, xs, (size_t)d->N * d->C, d->H, d->W, d->S, d->pad_w, st);
+      int rc = launch_shift_copies(x, xs, (size_t)d->N * d->C, d->H, d->W, d->S, d->pad_w, cs, st);
       if (rc) return rc;
       xb = reinterpret_cast<const __nv_bfloat16*>(xs);
     }
-    return run_wgrad(xb, dyb, dw, d->K, d->C, d->N, d->H, d->W, d->R, d->S, d->pad_h, st);
+    return run_wgrad(xb, dyb, dw, d->K, d->C, d->N, d->H / cs, d->W / cs, d->H, d->R, d->S, d->pad_h, cs, copies, st);
   }
   if (is_s2(d)) {
     SPC_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(d, 2), "tcgen05 wgrad: workspace too small");
     void* xs = reinterpret_cast<void*>(align1k(reinterpret_cast<uintptr_t>(ws)));
     int rc = launch_resample(false, x, xs, (size_t)d->N * d->C, d->H, d->W, st);
     if (rc) return rc;
-    return run_wgrad(reinterpret_cast<const __nv_bfloat16*>(xs), dyb, dw, d->K, d->C, d->N, d->H / 2, d->W / 2, 1, 1, 0,
-                     st);
+    return run_wgrad(reinterpret_cast<const __nv_bfloat16*>(xs), dyb, dw, d->K, d->C, d->N, 1, (d->H / 2) * (d->W / 2), 1,
+                     1, 1, 0, 1, false, st);
   }
-  return run_wgrad(xb, dyb, dw, d->K, d->C, d->N, 1, d->H * d->W, 1, 1, 0, st);
+  return run_wgrad(xb, dyb, dw, d->K, d->C, d->N, 1, d->H * d->W, 1, 1, 1, 0, 1, false, st);
 }
 
 }  // namespace spc

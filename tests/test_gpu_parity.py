@@ -150,6 +150,9 @@ CONV_CASES = [
     (1664, 416, (1, 1), (1, 1), 8, 48, False),    # 4 M-blocks, streamed weights
     (416, 1248, (1, 1), (1, 1), 8, 32, False),    # > 512 output channels: M groups
     (104, 208, (1, 1), (2, 2), 16, 64, False),    # stride-2 pointwise (FactorizedReduce)
+    (52, 52, (3, 3), (2, 2), 32, 256, False),     # stride-2 3x3 on tcgen05 (column-subsampled copies)
+    (104, 104, (3, 3), (2, 2), 8, 128, False),
+    (3, 104, (3, 3), (2, 2), 16, 128, False),     # the AmoebaNet stem
 ]
 
 
