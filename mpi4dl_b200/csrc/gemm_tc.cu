@@ -814,7 +814,6 @@ bool tap_shape_ok(const spc_conv_desc* d) {   // odd RxS "same" convs, stride 1 
   if (s2 && (d->H % 2 || d->W % 2)) return false;
   const int Wo = d->W / d->stride_w;
   if (Wo % 64 != 0) return false;
-  if ((size_t)d->S * d->N * (d->C > d->K ? d->C : d->K) * d->H * Wo * 2 > (8ull << 30)) return false;
   return (long long)d->H * d->W < (1ll << 31);
 }
 
@@ -837,6 +836,7 @@ bool pw_shape_ok(const spc_conv_desc* d) {
 bool tc_supported(const spc_conv_desc* d, int op) {
   if (pw_shape_ok(d)) return true;
   if (tap_shape_ok(d)) {
+    if (tc_workspace_bytes(d, op) > (24ull << 30)) return false;   // shifted copies would not fit comfortably
     if (op == 1 && is_s2(d)) return d->R == 3 && d->S == 3 && 4 * d->C <= 2048;   // parity-class dgrad
     return true;
   }
