@@ -136,9 +136,8 @@ def run_reference(args):
     scale = args.cpu_scale
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        rp.run_workload(d["layers"], scale)
-    times = [rp.run_workload(d["layers"], scale) for _ in range(max(1, min(args.steps, 5)))]
+    rp.run_workload(d["layers"], scale)              # warm-up (primitive creation per shape)
+    times = [rp.run_workload(d["layers"], scale, warm=False) for _ in range(max(1, min(args.steps, 5)))]
     t = statistics.median(times)
     # the sample is the same layer list at 1/scale linear size: work per image scales with scale^2
     val = 1.0 / (t * scale * scale)
@@ -165,7 +164,7 @@ def main():
     ap.add_argument("--workload", default="amoebanet", choices=list(WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--image", type=int, default=0, help="override the full image edge (debug)")
-    ap.add_argument("--cpu-scale", type=int, default=16, help="linear down-scale of the CPU baseline sample")
+    ap.add_argument("--cpu-scale", type=int, default=32, help="linear down-scale of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--algo", default="auto", choices=["auto", "direct"])
     args = ap.parse_args()
@@ -312,10 +311,9 @@ def main():
     step(True)
     ms_e2e = timed(args.steps, True)
 
-    # ---- per-kernel timing pass (CUDA events around single ops) -> roofline ----------------------
-    kinds = {}
-
-    def ev_time(fn, reps=1):
+    # ---- per-kernel timing pass: every distinct layer-op through the C ABI, CUDA events ----------
+    def ev_time(fn, reps=3):
+        fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -325,52 +323,56 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    per_layer = []
+    sp = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    kinds = {}
+    ops = []      # one record per (distinct layer, op)
     for key, u in uniq.items():
         l = u["layer"]
-        x = view(scratch_x, u["in_shape"]).detach().requires_grad_(not u["first"])
+        x = view(scratch_x, u["in_shape"])
         gy = view(scratch_gy, u["out_shape"])
-        yy = [None]
-
-        def f_fwd():
-            yy[0] = u["mod"](x)
-
-        t_f = ev_time(f_fwd)
-
-        def f_bwd():
-            yy[0].backward(gy, retain_graph=True)
-            x.grad = None
-
-        t_b = ev_time(f_bwd)
+        y = torch.empty(u["out_shape"], dtype=dtype, device=dev)
+        dx = torch.empty(u["in_shape"], dtype=dtype, device=dev)
+        recs = []
         if l["op"] == "conv":
-            bf = conv_bytes_flops(l, u["th"], u["tw"], esz)
+            w = u["mod"].weight.detach()
             dsc = _lib.ConvDesc(1, l["C"], u["th"], u["tw"], l["K"], l["R"], l["S"], l["stride_h"], l["stride_w"],
                                 l["pad_h"], l["pad_w"], _lib.dtype_code(dtype), algo)
-            tc = [L.spc_conv_uses_tcgen05(C.byref(dsc), op) for op in range(3)]
-            kname = "conv_fwd_" + ("tcgen05" if tc[0] else "direct")
-            byts, fl = bf["fwd"]
-            nb = 1 if u["first"] else 2
-            bb = bf["wgrad"][0] + (0 if u["first"] else bf["dgrad"][0])
-            fb = bf["wgrad"][1] + (0 if u["first"] else bf["dgrad"][1])
-            kb = "conv_bwd_" + ("tcgen05" if tc[2] else "direct")
-            u["mod"].weight.grad = None
+            nb = max(L.spc_conv_workspace_bytes(C.byref(dsc), i) for i in range(3))
+            ws = torch.empty(nb + 16, dtype=torch.uint8, device=dev)
+            dw = torch.zeros(w.shape, dtype=torch.float32, device=dev)
+            bf = conv_bytes_flops(l, u["th"], u["tw"], esz)
+            tc = [bool(L.spc_conv_uses_tcgen05(C.byref(dsc), i)) for i in range(3)]
+            fns = [("fprop", lambda: _lib.check(L.spc_conv2d_fwd(C.byref(dsc), vp(x), None, vp(w), None, vp(y), vp(ws), nb, sp()), "fwd"), bf["fwd"], tc[0])]
+            if not u["first"]:
+                fns.append(("dgrad", lambda: _lib.check(L.spc_conv2d_dgrad(C.byref(dsc), vp(gy), vp(w), vp(dx), vp(ws), nb, sp()), "dgrad"), bf["dgrad"], tc[1]))
+            fns.append(("wgrad", lambda: _lib.check(L.spc_conv2d_wgrad(C.byref(dsc), vp(x), None, vp(gy), vp(dw), None, 0, vp(ws), nb, sp()), "wgrad"), bf["wgrad"], tc[2]))
+            for nm, fn, (by, fl), is_tc in fns:
+                kern = ("pw_wgrad_kernel" if nm == "wgrad" else "pw_gemm_kernel") if is_tc else \
+                       ("wgrad_direct_kernel" if nm == "wgrad" else "conv_direct_kernel")
+                recs.append((nm, kern, ev_time(fn), by, fl))
+            shape = "%d->%d %dx%d s%d @%dx%d" % (l["C"], l["K"], l["R"], l["S"], l["stride_h"], u["th"], u["tw"])
         else:
+            mode = _lib.SPC_POOL_MAX if l["mode"] == "max" else _lib.SPC_POOL_AVG
+            dsc = _lib.PoolDesc(1, l["C"], u["th"], u["tw"], l["k"], l["stride"], l["pad"], mode, _lib.dtype_code(dtype))
             pb = pool_bytes(l, u["th"], u["tw"], esz)
-            kname, (byts, fl) = "pool_fwd", pb["fwd"]
-            kb, (bb, fb) = "pool_bwd", pb["bwd"]
-        for kn, tt, by, f in ((kname, t_f, byts, fl), (kb, t_b, bb, fb)):
-            k = kinds.setdefault(kn, dict(ms=0.0, bytes=0.0, flops=0.0, launches=0))
-            k["ms"] += tt * u["count"]
+            recs.append(("pool_fwd", "pool_fwd", ev_time(lambda: _lib.check(L.spc_pool2d_fwd(C.byref(dsc), vp(x), None, vp(y), sp()), "pool")), *pb["fwd"]))
+            recs.append(("pool_bwd", "pool_bwd", ev_time(lambda: _lib.check(L.spc_pool2d_bwd(C.byref(dsc), vp(x), None, vp(gy), vp(dx), sp()), "poolb")), *pb["bwd"]))
+            shape = "%s%d s%d C=%d @%dx%d" % (l["mode"], l["k"], l["stride"], l["C"], u["th"], u["tw"])
+        for nm, kern, ms, by, fl in recs:
+            ops.append(dict(shape=shape, op=nm, kernel=kern, count=u["count"], ms=ms, bytes=by, flops=fl))
+            k = kinds.setdefault(kern, dict(ms=0.0, bytes=0.0, flops=0.0, launches=0))
+            k["ms"] += ms * u["count"]
             k["bytes"] += by * u["count"]
-            k["flops"] += f * u["count"]
+            k["flops"] += fl * u["count"]
             k["launches"] += u["count"]
-        per_layer.append(dict(layer={k: v for k, v in l.items() if k in ("op", "C", "K", "R", "S", "stride_h", "k", "stride", "mode", "H", "W")},
-                              count=u["count"], fwd_ms=round(t_f, 3), bwd_ms=round(t_b, 3)))
-        del yy
+        del y, dx
 
     hbm, tfs, peak_src = peaks()
-    dom = max(kinds.items(), key=lambda kv: kv[1]["ms"])
-    dk = dom[1]
+    # dominant kernel = the kernel with the largest share of the step; its roofline entry is the
+    # launch-weighted aggregate over all its launches in one step (algorithmic bytes or flops of
+    # those launches / their summed CUDA-event durations)
+    dom_name, dk = max(kinds.items(), key=lambda kv: kv[1]["ms"])
     t_hbm = dk["bytes"] / (hbm * 1e9)
     t_tc = dk["flops"] / (tfs * 1e12)
     if t_hbm >= t_tc:
@@ -378,16 +380,33 @@ def main():
     else:
         roof = {"bound": "tensor", "achieved": dk["flops"] / (dk["ms"] * 1e-3) / 1e12, "peak": tfs, "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["traffic"] = None
-    roof["kernel"] = dom[0]
+    roof["kernel"] = dom_name
+    roof["launches_per_step"] = dk["launches"]
     roof["peak_source"] = peak_src
     roof["share_of_step"] = dk["ms"] / sum(k["ms"] for k in kinds.values())
-    # whole-step roofline (BASELINE.md definition: sum_layers max(F/P, B/BW) / n_gpus)
-    t_roof = sum(max(k["bytes"] / (hbm * 1e9), k["flops"] / (tfs * 1e12)) for k in kinds.values())
+    # DRAM traffic of that kernel from the committed ncu --set full capture (profiles/), for the
+    # heaviest single launch shape of the kernel, next to the same launch's algorithmic bytes
+    roof["traffic"] = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        cand = sorted((o for o in ops if o["kernel"] == dom_name), key=lambda o: -o["ms"] * o["count"])
+        for o in cand:
+            kk = o["shape"] + " " + o["op"]
+            if kk in tr:
+                roof["traffic"] = tr[kk]["dram_bytes"]
+                roof["traffic_launch"] = {"launch": kk, "algorithmic_bytes": o["bytes"], "event_ms": round(o["ms"], 4),
+                                          "achieved_GBps": round(o["bytes"] / o["ms"] / 1e6, 1), "ncu": tr[kk].get("source")}
+                break
+    except Exception:
+        pass
+    # whole-step roofline (sum over layer-ops of max(F/P, B/BW))
+    t_roof = sum(o["count"] * max(o["bytes"] / (hbm * 1e9), o["flops"] / (tfs * 1e12)) for o in ops)
     roof["step_roofline_ms"] = t_roof * 1e3
     roof["step_frac"] = t_roof * 1e3 / (ms_total / args.steps)
-    roof["kinds"] = {k: dict(ms=round(v["ms"], 3), GBps=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+    roof["kinds"] = {k: dict(ms=round(v["ms"], 3), launches=v["launches"], GBps=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
                              TFLOPs=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)) for k, v in kinds.items()}
+    per_layer = [dict(shape=o["shape"], op=o["op"], kernel=o["kernel"], count=o["count"], ms=round(o["ms"], 4),
+                      GBps=round(o["bytes"] / o["ms"] / 1e6, 1), TFLOPs=round(o["flops"] / o["ms"] / 1e9, 1)) for o in ops]
 
     if rank == 0:
         cpu = None
@@ -396,11 +415,12 @@ def main():
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
             scale = args.cpu_scale * shrink
-            rp.run_workload(d["layers"], scale)
             tcpu = rp.run_workload(d["layers"], scale)
             cpu = {"value": 1.0 / (tcpu * (scale / shrink) ** 2), "unit": "images/sec", "cores": cores, "kind": "port",
-                   "sample": "all %d layers fwd+bwd at 1/%d linear size in fp32 with the torch CPU ops the reference calls "
-                             "(oracle/ref_port_torch.py), %.1f s, extrapolated by area" % (len(d["layers"]), scale, tcpu)}
+                   "sample": "all %d layers fwd+bwd at 1/%d linear size (%dx%d image) in fp32 with the torch CPU ops the "
+                             "reference calls (oracle/ref_port_torch.py; per-shape warm-up excluded), %.1f s timed, "
+                             "extrapolated by area x%d" % (len(d["layers"]), scale, image // args.cpu_scale, image // args.cpu_scale,
+                                                          tcpu, (scale // shrink) ** 2)}
         ms_step = ms_total / args.steps
         out = {
             "metric": METRIC, "value": 1000.0 / ms_step, "unit": "images/sec", "n_gpus": world, "steps": args.steps,

@@ -44,12 +44,19 @@ def run_layer(layer, scale, dtype=torch.float32, first=False):
     return time.perf_counter() - t0, 0.0
 
 
-def run_workload(layers, scale, threads=None):
-    """One pass (fwd+bwd of every layer) at 1/scale linear size.  Returns seconds."""
+def run_workload(layers, scale, threads=None, warm=True):
+    """One pass (fwd+bwd of every layer) at 1/scale linear size.  Each distinct layer is run once
+    untimed first (oneDNN primitive creation / JIT per new shape is not part of the steady-state
+    step), then timed.  Returns seconds of the timed pass."""
     if threads:
         torch.set_num_threads(threads)
     total = 0.0
+    seen = set()
     for i, l in enumerate(layers):
+        key = tuple(sorted((k, str(v)) for k, v in l.items()))
+        if warm and key not in seen:
+            run_layer(l, scale, first=(i == 0))
+            seen.add(key)
         dt, _ = run_layer(l, scale, first=(i == 0))
         total += dt
     return total
