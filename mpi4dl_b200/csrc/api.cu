@@ -51,6 +51,7 @@ int fwd_rect(DirectConvParams p, int dtype, int y0, int y1, int x0, int x1, cuda
   p.oy0 = y0; p.ox0 = x0;
   p.pt -= y0 * p.sh; p.pl -= x0 * p.sw;
   p.Ho = y1 - y0; p.Wo = x1 - x0;
+  p.vert = (p.Wo <= 16 && p.Ho > p.Wo) ? 1 : 0;   // thin column strip: 128-row x 8-col CTA tiles
   return launch_conv_direct(p, dtype, st);
 }
 
@@ -198,18 +199,8 @@ int spc_conv2d_wgrad(const spc_conv_desc* d, const void* x, const spc_halo* halo
       // strips (interior reads as zero) -- exact by linearity -- restricted to the output strips
       // whose windows reach outside the tile.
       p.in = make_view(nullptr, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);
-      const int top = min(Ho, ceil_div(d->pad_h, d->stride_h));
-      const int bot0 = max(top, min(Ho, ceil_div(d->H + d->pad_h - d->R + 1, d->stride_h)));
-      const int left = min(Wo, ceil_div(d->pad_w, d->stride_w));
-      const int right0 = max(left, min(Wo, ceil_div(d->W + d->pad_w - d->S + 1, d->stride_w)));
-      const int rects[4][4] = {{0, 0, top, Wo}, {bot0, 0, Ho - bot0, Wo}, {top, 0, bot0 - top, left},
-                               {top, right0, bot0 - top, Wo - right0}};
-      for (int i = 0; i < 4; ++i) {
-        if (rects[i][2] <= 0 || rects[i][3] <= 0) continue;
-        p.ry0 = rects[i][0]; p.rx0 = rects[i][1]; p.rH = rects[i][2]; p.rW = rects[i][3];
-        rc = launch_wgrad_direct(p, d->dtype, st);
-        if (rc) return rc;
-      }
+      rc = launch_wgrad_halo(p, d->dtype, st);
+      if (rc) return rc;
     }
   } else {
     p.in = make_view(x, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);

@@ -94,6 +94,7 @@ struct DirectConvParams {
   int Ho, Wo;                       // logical output extent of this launch
   int YH, YW, oy0, ox0, oys, oxs;   // physical output tensor and mapping
   long long w_off, wKs, wCs, wRs, wSs;
+  int vert;                         // 1: CTA tile is 128 rows x 8 cols (thin column strips) instead of 8 x 128
 };
 int launch_conv_direct(const DirectConvParams& p, int dtype, cudaStream_t st);
 
@@ -105,6 +106,8 @@ struct DirectWgradParams {
   int ry0, rx0, rH, rW;   // output sub-rectangle to reduce over (rH == 0: the whole output)
 };
 int launch_wgrad_direct(const DirectWgradParams& p, int dtype, cudaStream_t st);
+// dw += contribution of the halo pixels only (boundary output pixels x taps that fall outside the tile)
+int launch_wgrad_halo(const DirectWgradParams& p, int dtype, cudaStream_t st);
 int launch_bias_grad(const void* dy, float* db, int N, int K, int HW, int dtype, int accumulate, cudaStream_t st);
 
 // ---- tcgen05 pointwise GEMM path: gemm_tc.cu ---------------------------------------------

@@ -16,23 +16,27 @@ constexpr int DC_TH = 8;        // output rows per CTA (one warp per row)
 constexpr int DC_LANES = 32;    // threads along W
 constexpr int DC_PX = 4;        // output pixels per thread (col = lane + 32*j)
 constexpr int DC_TW = DC_LANES * DC_PX;
-constexpr int DC_KB = 16;       // output channels per CTA
+// output channels per CTA: 16 (whole-tile launches) or 4 (thin boundary strips: 4x more CTAs)
 constexpr int DC_THREADS = DC_TH * DC_LANES;
 
-template <typename T>
+// VERT = false: CTA output tile 8 rows x 128 cols (lanes along W).  VERT = true: 128 rows x 8
+// cols (lanes along H) for the thin left/right boundary strips.
+template <typename T, bool VERT, int DC_KB>
 __global__ void __launch_bounds__(DC_THREADS)
 conv_direct_kernel(const DirectConvParams p, const int CB, const int tiles_x, const int kblocks) {
   extern __shared__ float smem[];
-  const int PH = (DC_TH - 1) * p.sh + p.R;
-  const int PW = (DC_TW - 1) * p.sw + p.S;
+  constexpr int TILE_H = VERT ? DC_TW : DC_TH;
+  constexpr int TILE_W = VERT ? DC_TH : DC_TW;
+  const int PH = (TILE_H - 1) * p.sh + p.R;
+  const int PW = (TILE_W - 1) * p.sw + p.S;
   const int PWp = PW | 1;  // odd pitch
   float* patch = smem;                          // [CB][PH][PWp]
   float* wsm = smem + (((size_t)CB * PH * PWp + 3) & ~(size_t)3);  // [CB][R][S][DC_KB], 16B aligned
 
   const int kb = blockIdx.x % kblocks;
   const int tile = blockIdx.x / kblocks;
-  const int tx0 = (tile % tiles_x) * DC_TW;
-  const int ty0 = (tile / tiles_x) * DC_TH;
+  const int tx0 = (tile % tiles_x) * TILE_W;
+  const int ty0 = (tile / tiles_x) * TILE_H;
   const int n = blockIdx.y;
   const int k0 = kb * DC_KB;
   const int lane = threadIdx.x % DC_LANES;
@@ -80,12 +84,14 @@ conv_direct_kernel(const DirectConvParams p, const int CB, const int tiles_x, co
     const int cmax = min(CB, C - c0);
     for (int c = 0; c < cmax; ++c) {
       for (int r = 0; r < p.R; ++r) {
-        const float* prow = patch + (c * PH + ty * p.sh + r) * PWp;
+        const float* prow = patch + (c * PH + (VERT ? 0 : ty * p.sh) + r) * PWp;
         const float* wrow = wsm + (c * RS + r * p.S) * DC_KB;
         for (int s = 0; s < p.S; ++s) {
           float xv[DC_PX];
 #pragma unroll
-          for (int j = 0; j < DC_PX; ++j) xv[j] = prow[(lane + DC_LANES * j) * p.sw + s];
+          for (int j = 0; j < DC_PX; ++j)
+            xv[j] = VERT ? prow[((lane + DC_LANES * j) * p.sh) * PWp + ty * p.sw + s]
+                         : prow[(lane + DC_LANES * j) * p.sw + s];
           const float4* wv = reinterpret_cast<const float4*>(wrow + s * DC_KB);
           float wk[DC_KB];
 #pragma unroll
@@ -102,18 +108,18 @@ conv_direct_kernel(const DirectConvParams p, const int CB, const int tiles_x, co
     }
   }
 
-  const int oy = ty0 + ty;
-  if (oy >= p.Ho) return;
   T* y = reinterpret_cast<T*>(p.y);
 #pragma unroll
   for (int k = 0; k < DC_KB; ++k) {
     if (k0 + k >= p.K) break;
     const float b = p.bias ? to_f32<T>(reinterpret_cast<const T*>(p.bias)[k0 + k]) : 0.f;
-    const size_t row = (((size_t)n * p.K + (k0 + k)) * p.YH + (p.oy0 + oy * p.oys)) * p.YW;
+    const size_t plane = ((size_t)n * p.K + (k0 + k)) * p.YH;
 #pragma unroll
     for (int j = 0; j < DC_PX; ++j) {
-      const int ox = tx0 + lane + DC_LANES * j;
-      if (ox < p.Wo) y[row + p.ox0 + ox * p.oxs] = from_f32<T>(acc[j][k] + b);
+      const int oy = VERT ? ty0 + lane + DC_LANES * j : ty0 + ty;
+      const int ox = VERT ? tx0 + ty : tx0 + lane + DC_LANES * j;
+      if (oy < p.Ho && ox < p.Wo)
+        y[(plane + (p.oy0 + oy * p.oys)) * p.YW + p.ox0 + ox * p.oxs] = from_f32<T>(acc[j][k] + b);
     }
   }
 }
@@ -225,8 +231,12 @@ __global__ void bias_grad_kernel(const T* __restrict__ dy, float* __restrict__ d
 
 int launch_conv_direct(const DirectConvParams& p, int dtype, cudaStream_t st) {
   if (p.Ho <= 0 || p.Wo <= 0 || p.in.N <= 0) return SPC_OK;
-  const int PH = (DC_TH - 1) * p.sh + p.R;
-  const int PW = ((DC_TW - 1) * p.sw + p.S) | 1;
+  const int TILE_H = p.vert ? DC_TW : DC_TH, TILE_W = p.vert ? DC_TH : DC_TW;
+  const int PH = (TILE_H - 1) * p.sh + p.R;
+  const int PW = ((TILE_W - 1) * p.sw + p.S) | 1;
+  // thin strips (boundary fix-up) have few output pixels: use 4 output channels per CTA so that
+  // the launch still fills the machine
+  const int DC_KB = ((long long)p.Ho * p.Wo * p.in.N <= 64 * 1024) ? 4 : 16;
   int CB = p.in.C < 8 ? p.in.C : 8;
   auto bytes = [&](int cb) {
     return ((((size_t)cb * PH * PW + 3) & ~(size_t)3) + (size_t)cb * p.R * p.S * DC_KB) * sizeof(float);
@@ -234,18 +244,110 @@ int launch_conv_direct(const DirectConvParams& p, int dtype, cudaStream_t st) {
   while (CB > 1 && bytes(CB) > 96 * 1024) CB >>= 1;
   const size_t smem = bytes(CB);
   SPC_REQUIRE(smem <= 200 * 1024, "conv_direct: filter %dx%d stride %d needs %zu B smem", p.R, p.S, p.sh, smem);
-  const int tiles_x = ceil_div(p.Wo, DC_TW), tiles_y = ceil_div(p.Ho, DC_TH);
+  const int tiles_x = ceil_div(p.Wo, TILE_W), tiles_y = ceil_div(p.Ho, TILE_H);
   const int kblocks = ceil_div(p.K, DC_KB);
   dim3 grid((unsigned)((size_t)tiles_x * tiles_y * kblocks), p.in.N);
+#define SPC_LAUNCH_DC2(TT, VV, KK)                                                                                  \
+  do {                                                                                                               \
+    SPC_CHECK_CUDA(cudaFuncSetAttribute(conv_direct_kernel<TT, VV, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                        200 * 1024));                                                                \
+    conv_direct_kernel<TT, VV, KK><<<grid, DC_THREADS, smem, st>>>(p, CB, tiles_x, kblocks);                         \
+  } while (0)
+#define SPC_LAUNCH_DC(TT, VV)                                          \
+  do {                                                                 \
+    if (DC_KB == 4) SPC_LAUNCH_DC2(TT, VV, 4); else SPC_LAUNCH_DC2(TT, VV, 16); \
+  } while (0)
   if (dtype == SPC_BF16) {
-    SPC_CHECK_CUDA(cudaFuncSetAttribute(conv_direct_kernel<__nv_bfloat16>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    conv_direct_kernel<__nv_bfloat16><<<grid, DC_THREADS, smem, st>>>(p, CB, tiles_x, kblocks);
+    if (p.vert) SPC_LAUNCH_DC(__nv_bfloat16, true); else SPC_LAUNCH_DC(__nv_bfloat16, false);
   } else {
-    SPC_CHECK_CUDA(cudaFuncSetAttribute(conv_direct_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        200 * 1024));
-    conv_direct_kernel<float><<<grid, DC_THREADS, smem, st>>>(p, CB, tiles_x, kblocks);
+    if (p.vert) SPC_LAUNCH_DC(float, true); else SPC_LAUNCH_DC(float, false);
   }
+#undef SPC_LAUNCH_DC
+#undef SPC_LAUNCH_DC2
+  spc::count_launch();
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Halo-only wgrad correction: dw[k][c][tap] += sum over boundary output pixels p and taps whose
+// input pixel lies OUTSIDE the tile of dy[k][p] * halo(c, pixel).  One thread per (k, c) pair of a
+// 16 x 16 block; blockIdx.y walks chunks of the boundary-pixel list; whether a (pixel, tap) pair is
+// outside is uniform across the block, so there is no divergence.
+constexpr int WH_TG = 8;   // taps per register pass
+template <typename T>
+__global__ void __launch_bounds__(256)
+wgrad_halo_kernel(const DirectWgradParams p, const int kblocks, const int npix, const int pix_per_cta, const int top,
+                  const int bot0, const int left, const int right0) {
+  const int kb = blockIdx.x % kblocks, cb = blockIdx.x / kblocks;
+  const int k = kb * 16 + threadIdx.x / 16, c = cb * 16 + threadIdx.x % 16;
+  const int C = p.in.C, taps = p.R * p.S;
+  const bool active = k < p.K && c < C;
+  const T* dy = reinterpret_cast<const T*>(p.dy);
+  // boundary pixel list = top band rows [0,top) | bottom band [bot0,Ho) | left cols | right cols (middle rows)
+  const int n_top = top * p.Wo, n_bot = (p.Ho - bot0) * p.Wo, mid = bot0 - top;
+  const int n_left = mid * left, wr = p.Wo - right0;
+  const int per_image = n_top + n_bot + n_left + mid * wr;
+  const int q0 = blockIdx.y * pix_per_cta, q1 = min(npix, q0 + pix_per_cta);
+  for (int tg = 0; tg < taps; tg += WH_TG) {
+    const int r_first = tg / p.S, s_first = tg % p.S;
+    float acc[WH_TG];
+#pragma unroll
+    for (int u = 0; u < WH_TG; ++u) acc[u] = 0.f;
+    for (int q = q0; q < q1; ++q) {
+      const int n = q / per_image;
+      int e = q - n * per_image, oy, ox;
+      if (e < n_top) { oy = e / p.Wo; ox = e - oy * p.Wo; }
+      else if ((e -= n_top) < n_bot) { oy = e / p.Wo; ox = e - oy * p.Wo; oy += bot0; }
+      else if ((e -= n_bot) < n_left) { oy = e / left; ox = e - oy * left; oy += top; }
+      else { e -= n_left; oy = e / wr; ox = right0 + e - oy * wr; oy += top; }
+      const int h0 = oy * p.sh - p.ph, w0 = ox * p.sw - p.pw;
+      // does any tap of this pass fall outside the tile? (block-uniform)  rows h0+r, cols w0+s
+      float g = 0.f;
+      bool loaded = false;
+      int r = r_first, sx = s_first;
+#pragma unroll
+      for (int u = 0; u < WH_TG; ++u) {
+        if (tg + u < taps) {
+          const int h = h0 + r, w = w0 + sx;
+          if ((unsigned)h >= (unsigned)p.in.H || (unsigned)w >= (unsigned)p.in.W) {
+            if (!loaded) {
+              g = active ? to_f32<T>(dy[(((size_t)n * p.K + k) * p.Ho + oy) * p.Wo + ox]) : 0.f;
+              loaded = true;
+            }
+            if (active) acc[u] = fmaf(g, tile_load<T>(p.in, n, c, h, w), acc[u]);
+          }
+          if (++sx == p.S) { sx = 0; ++r; }
+        }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int u = 0; u < WH_TG; ++u)
+        if (tg + u < taps && acc[u] != 0.f) atomicAdd(&p.dw[((size_t)k * C + c) * taps + tg + u], acc[u]);
+    }
+  }
+}
+
+int launch_wgrad_halo(const DirectWgradParams& p, int dtype, cudaStream_t st) {
+  const int top = min(p.Ho, ceil_div(p.ph, p.sh));
+  const int bot0 = max(top, min(p.Ho, ceil_div(p.in.H + p.ph - p.R + 1, p.sh)));
+  const int left = min(p.Wo, ceil_div(p.pw, p.sw));
+  const int right0 = max(left, min(p.Wo, ceil_div(p.in.W + p.pw - p.S + 1, p.sw)));
+  const int per_image = top * p.Wo + (p.Ho - bot0) * p.Wo + (bot0 - top) * (left + p.Wo - right0);
+  const long long npix = (long long)per_image * p.in.N;
+  if (npix <= 0) return SPC_OK;
+  const int kblocks = ceil_div(p.K, 16), cblocks = ceil_div(p.in.C, 16);
+  int chunks = (int)((npix + 255) / 256);
+  const int max_chunks = (148 * 8 + kblocks * cblocks - 1) / (kblocks * cblocks);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  const int pix_per_cta = (int)((npix + chunks - 1) / chunks);
+  dim3 grid(kblocks * cblocks, chunks);
+  if (dtype == SPC_BF16)
+    wgrad_halo_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, kblocks, (int)npix, pix_per_cta, top, bot0, left, right0);
+  else
+    wgrad_halo_kernel<float><<<grid, 256, 0, st>>>(p, kblocks, (int)npix, pix_per_cta, top, bot0, left, right0);
   spc::count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
