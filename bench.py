@@ -171,6 +171,10 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # keep stdout clean for the ONE JSON line (NCCL / torchrun banners go to stderr)
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -440,7 +444,7 @@ def main():
             "cpu_baseline": cpu,
             "per_layer": per_layer,
         }
-        print(json.dumps(out))
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
