@@ -13,6 +13,8 @@
 // wgrad:       both operands K-major straight from NCHW (pixels = reduction dim, contiguous).
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
 // warps 2..5 = epilogue (TMEM -> registers -> global).  Persistent CTAs, one per SM.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -110,6 +112,7 @@ struct PwParams {
   int W, Mpad;                 // image width (tap mode: tiles are 64-pixel row segments), padded M
   int shiftN;                  // N when the activations are S column-shifted copies, else 0
   int rowmul;                  // input row = rowmul * output row + tap row offset (2 for stride-2 convs)
+  int tgroup;                  // consecutive tiles handled back-to-back by one CTA (DRAM page locality)
   const __nv_bfloat16* bias;   // [M] or null
 };
 
@@ -166,7 +169,10 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                         (it / kchunks) * p.Mpad + mb * 128);
       }
       int s = 0, ph = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      for (int it = 0;; ++it) {
+        const int t = ((it / p.tgroup) * gridDim.x + blockIdx.x) * p.tgroup + it % p.tgroup;
+        if ((it / p.tgroup) * gridDim.x * p.tgroup >= p.num_tiles) break;
+        if (t >= p.num_tiles) continue;
         const int mg = t % p.num_mg;
         const int tt = t / p.num_mg;
         const int n = tt / p.tiles_per_image;
@@ -205,7 +211,10 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       constexpr uint32_t IDESC = umma_idesc_bf16(128, BN, /*a_mn=*/0, /*b_mn=*/1);
       if (p.wres) { mbar_wait(wfull, 0); tc_fence_after(); }
       int s = 0, ph = 0, a = 0, aph = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      for (int it = 0;; ++it) {
+        const int t = ((it / p.tgroup) * gridDim.x + blockIdx.x) * p.tgroup + it % p.tgroup;
+        if ((it / p.tgroup) * gridDim.x * p.tgroup >= p.num_tiles) break;
+        if (t >= p.num_tiles) continue;
         mbar_wait(&tempty[a], aph ^ 1);
         tc_fence_after();
         for (int it = 0; it < iters; ++it) {
@@ -239,7 +248,10 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     const int row = quarter * 32 + lane;   // row of the 128-channel block (= TMEM lane)
     const bool leader = (threadIdx.x == 64);
     int a = 0, aph = 0, ob = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int it = 0;; ++it) {
+      const int t = ((it / p.tgroup) * gridDim.x + blockIdx.x) * p.tgroup + it % p.tgroup;
+      if ((it / p.tgroup) * gridDim.x * p.tgroup >= p.num_tiles) break;
+      if (t >= p.num_tiles) continue;
       const int mg = t % p.num_mg;
       const int tt = t / p.num_mg;
       const int n = tt / p.tiles_per_image;
@@ -320,6 +332,7 @@ int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& t
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  if (p.num_tiles < 16 * sms) p.tgroup = 1;   // small problems: keep every SM busy
   kern<<<grid, TC_THREADS, smem, st>>>(tw, tx, tx4, ty, p);
   count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
@@ -412,6 +425,11 @@ int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bi
   p.taps = taps; p.S = c.S; p.ph = c.ph; p.pw = c.pw; p.W = Wo; p.Mpad = Mpad;
   p.shiftN = copies ? c.N : 0;
   p.rowmul = cs;
+  {
+    const char* e = getenv("SPC_TILE_GROUP");
+    p.tgroup = e ? atoi(e) : 1;   // measured: no effect on B200 (tools/stride_probe.py), kept as a knob
+    if (p.tgroup < 1) p.tgroup = 1;
+  }
   const int MBtot = Mpad / 128;
   p.num_mg = (Mpad + 511) / 512;
   p.tiles_per_image = (P + BN - 1) / BN;
