@@ -810,7 +810,97 @@ __global__ void shift_copies_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
     *reinterpret_cast<uint4*>(xs + ((size_t)sidx * rows + row) * Wv + v * 8) = *reinterpret_cast<const uint4*>(e);
   }
 }
+// Fast path, stride 1: one thread produces the 8-pixel vector of ALL S copies from three aligned
+// 16-byte loads (previous / own / next vector); a copy shifted by `off` columns is a 16-bit
+// funnel shift of that 24-element window.  |s - pw| <= 8.
+template <int S, int PW>
+__global__ void __launch_bounds__(256)
+shift_copies_vec_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xs, size_t planes, int H,
+                        int W) {
+  const int wv = W / 8;
+  const size_t rows = planes * H;
+  const size_t total = rows * wv;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % wv);
+    const size_t row = i / wv;
+    const uint4* src = reinterpret_cast<const uint4*>(x + row * W) + v;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const uint4 a = v > 0 ? __ldg(src - 1) : z;
+    const uint4 b = __ldg(src);
+    const uint4 c = v < wv - 1 ? __ldg(src + 1) : z;
+    const uint32_t win[13] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, 0u};
+#pragma unroll
+    for (int sidx = 0; sidx < S; ++sidx) {
+      const int e0 = 8 + sidx - PW;            // first element of the window [a|b|c]: compile-time
+      const int k = e0 >> 1;
+      uint4 o;
+      if (e0 & 1) {
+        o.x = __funnelshift_r(win[k], win[k + 1], 16);
+        o.y = __funnelshift_r(win[k + 1], win[k + 2], 16);
+        o.z = __funnelshift_r(win[k + 2], win[k + 3], 16);
+        o.w = __funnelshift_r(win[k + 3], win[k + 4], 16);
+      } else {
+        o.x = win[k]; o.y = win[k + 1]; o.z = win[k + 2]; o.w = win[k + 3];
+      }
+      *reinterpret_cast<uint4*>(xs + ((size_t)sidx * rows + row) * W + v * 8) = o;
+    }
+  }
+}
+// Fast path, stride 2, 3 filter columns, pw = 1: xs[s][j] = x[2j + s - 1]; 8 outputs per copy from the
+// own 16 input pixels plus the last pixel of the previous vector.
+__global__ void __launch_bounds__(256)
+shift_copies_s2k3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xs, size_t planes, int H,
+                         int W) {
+  const int Wv = W / 2, wv = Wv / 8;
+  const size_t rows = planes * H;
+  const size_t total = rows * wv;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % wv);
+    const size_t row = i / wv;
+    const uint4* src = reinterpret_cast<const uint4*>(x + row * W) + 2 * v;
+    const uint4 a = __ldg(src), b = __ldg(src + 1);
+    const uint32_t prev = v > 0 ? (__ldg(reinterpret_cast<const uint32_t*>(src) - 1) >> 16) : 0u;   // x[16v - 1]
+    uint4 ev, od, sh;
+    ev.x = __byte_perm(a.x, a.y, 0x5410); ev.y = __byte_perm(a.z, a.w, 0x5410);     // x[16v + 0,2,4,...]
+    ev.z = __byte_perm(b.x, b.y, 0x5410); ev.w = __byte_perm(b.z, b.w, 0x5410);
+    od.x = __byte_perm(a.x, a.y, 0x7632); od.y = __byte_perm(a.z, a.w, 0x7632);     // x[16v + 1,3,5,...]
+    od.z = __byte_perm(b.x, b.y, 0x7632); od.w = __byte_perm(b.z, b.w, 0x7632);
+    sh.x = (od.x << 16) | prev;                                                      // x[16v - 1, 1, 3, ...]
+    sh.y = __funnelshift_r(od.x, od.y, 16);
+    sh.z = __funnelshift_r(od.y, od.z, 16);
+    sh.w = __funnelshift_r(od.z, od.w, 16);
+    __nv_bfloat16* dst = xs + row * Wv + v * 8;
+    *reinterpret_cast<uint4*>(dst) = sh;                                  // s = 0: 2j - 1
+    *reinterpret_cast<uint4*>(dst + rows * Wv) = ev;                      // s = 1: 2j
+    *reinterpret_cast<uint4*>(dst + 2 * rows * Wv) = od;                  // s = 2: 2j + 1
+  }
+}
 int launch_shift_copies(const void* x, void* xs, size_t planes, int H, int W, int S, int pw, int cs, cudaStream_t st) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(xs) % 16 == 0);
+  if (aligned && cs == 1 && W % 8 == 0 &&
+      ((S == 7 && pw == 3) || (S == 3 && pw == 1) || (S == 5 && pw == 2) || (S == 2 && pw == 0))) {
+    const size_t tot = planes * H * (W / 8);
+    size_t blocks = (tot + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
+    __nv_bfloat16* xo = (__nv_bfloat16*)xs;
+    if (S == 7) shift_copies_vec_kernel<7, 3><<<(int)blocks, 256, 0, st>>>(xi, xo, planes, H, W);
+    else if (S == 3) shift_copies_vec_kernel<3, 1><<<(int)blocks, 256, 0, st>>>(xi, xo, planes, H, W);
+    else if (S == 5) shift_copies_vec_kernel<5, 2><<<(int)blocks, 256, 0, st>>>(xi, xo, planes, H, W);
+    else shift_copies_vec_kernel<2, 0><<<(int)blocks, 256, 0, st>>>(xi, xo, planes, H, W);
+    count_launch();
+    SPC_CHECK_CUDA(cudaGetLastError());
+    return SPC_OK;
+  }
+  if (aligned && cs == 2 && S == 3 && pw == 1 && W % 16 == 0) {
+    const size_t tot = planes * H * (W / 16);
+    size_t blocks = (tot + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    shift_copies_s2k3_kernel<<<(int)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)xs, planes, H, W);
+    count_launch();
+    SPC_CHECK_CUDA(cudaGetLastError());
+    return SPC_OK;
+  }
   const size_t total = planes * H * (W / cs / 8) * S;
   size_t blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;

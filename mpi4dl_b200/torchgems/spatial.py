@@ -211,11 +211,16 @@ class conv_spatial(nn.Conv2d, _SpatialTopology):
             padding = (padding, padding)
         self._init_topology(local_rank, spatial_size, num_spatial_parts, slice_method)
 
+        self.fused_halo = halo_len is not None
         if halo_len is not None:
+            # D2 "fused halo" variant (spatial.py:67-111): the tile already carries its halo (one wide
+            # halo_exchange_layer per block), so there is NO exchange here; only the sides that are
+            # true image borders get `padding` zeros, the sides facing a neighbour get none and the
+            # output shrinks there.  The reference hard-codes the 2x2 grid (ranks 0-3); here the
+            # border sides follow from the rank grid, which is the same table for square-4.
             assert halo_len == 0, "Error: Custom Halo Len is not supported (only halo_len=0 is supported)"
-            raise NotImplementedError(
-                "conv_spatial(halo_len=0) is the D2 fused-halo variant (reference spatial.py:67-111); "
-                "not built yet -- SURVEY.md section 8(f) item 3")
+            assert (kernel_size[0] - 1) // 2 == padding[0] and (kernel_size[1] - 1) // 2 == padding[1], \
+                "conv_spatial(halo_len=0): padding must be (k-1)//2"
         # spatial.py:115-121
         self.halo_len_height = int((kernel_size[0] - 1) / 2)
         self.halo_len_width = int((kernel_size[1] - 1) / 2)
@@ -232,8 +237,33 @@ class conv_spatial(nn.Conv2d, _SpatialTopology):
             if self.neighbours is not None:
                 self.set_neighbours_based_on_kernel_size()
                 self.get_neighbours_rank()
+        if self.fused_halo:
+            nb = self.neighbours or [0] * 9
+            # sides with a neighbour: (top, bottom, left, right)
+            self._inner_sides = (bool(nb[1]), bool(nb[7]), bool(nb[3]), bool(nb[5]))
+            self.halo_len_height_d2, self.halo_len_width_d2 = 0, 0
+            self.neighbours = None          # never exchanges
         self.set_tags()
         self.algo = _lib.SPC_ALGO_AUTO
+
+    def _crop_fused(self, y, H, W):
+        """Drop the output rows / columns whose window would reach past a neighbour-facing edge
+        (those sides carry no padding in the D2 variant)."""
+        R, S = self.kernel_size
+        sh, sw = self.stride
+        ph, pw = self.halo_len_height, self.halo_len_width
+        Ho, Wo = y.shape[2], y.shape[3]
+        top, bottom, left, right = self._inner_sides
+        if (top and ph % sh) or (left and pw % sw):
+            # an unpadded top/left edge shifts the sampling phase of a strided conv; that needs an
+            # asymmetric-pad kernel entry (next), cropping the "same" convolution is not equivalent
+            raise NotImplementedError("conv_spatial(halo_len=0) with stride > 1 on a tile whose top/left "
+                                      "side faces a neighbour is not supported yet")
+        y0 = -(-ph // sh) if top else 0                                   # first row with window start >= 0
+        y1 = min(Ho, (H - R + ph) // sh + 1) if bottom else Ho            # last row with window end < H
+        x0 = -(-pw // sw) if left else 0
+        x1 = min(Wo, (W - S + pw) // sw + 1) if right else Wo
+        return y[:, :, y0:y1, x0:x1]
 
     def forward(self, tensor):
         _require_cuda(tensor, "conv_spatial")
@@ -242,11 +272,14 @@ class conv_spatial(nn.Conv2d, _SpatialTopology):
             raise RuntimeError("conv_spatial: input dtype %s != weight dtype %s" % (x.dtype, self.weight.dtype))
         hh, hw = self.halo_len_height, self.halo_len_width
         with torch.no_grad():
-            strips = self._exchange(x, hh, hw) if (hh > 0 or hw > 0) else [None] * 9
+            strips = self._exchange(x, hh, hw) if ((hh > 0 or hw > 0) and not self.fused_halo) else [None] * 9
         N, Cc, H, W = x.shape
         desc_args = (N, Cc, H, W, self.out_channels, self.kernel_size[0], self.kernel_size[1], self.stride[0],
                      self.stride[1], hh, hw, _lib.dtype_code(x.dtype), self.algo)
-        return _ConvSpatialFn.apply(x, self.weight, self.bias, desc_args, *strips)
+        y = _ConvSpatialFn.apply(x, self.weight, self.bias, desc_args, *strips)
+        if self.fused_halo:
+            y = self._crop_fused(y, H, W)
+        return y
 
 
 class _HaloPadFn(torch.autograd.Function):

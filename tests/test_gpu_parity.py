@@ -281,3 +281,38 @@ def test_full_size_properties_linearity_and_tile_equals_slice():
     yp = _PoolFn.apply(left, (N, Cc, h, ww, 3, 1, 1, _lib.SPC_POOL_AVG, code), *([None] * 9))
     ref = torch.nn.functional.avg_pool2d(left.float(), 3, 1, 1, count_include_pad=True)
     assert torch.allclose(yp.float(), ref, atol=2e-2, rtol=2e-2)
+
+
+@pytest.mark.parametrize("rank", range(4))
+@pytest.mark.parametrize("k,stride", [((3, 3), 1), ((1, 7), 1), ((3, 3), 2)])
+def test_fused_halo_conv_variant(rank, k, stride):
+    """conv_spatial(halo_len=0) (D2): zero padding only on image-border sides, none (valid conv)
+    on neighbour-facing sides, no exchange.  Oracle: asymmetric np.pad + padding=0 conv."""
+    from mpi4dl_b200.torchgems import spatial
+
+    rng = np.random.default_rng(11 + rank)
+    C, K, H, W = 8, 6, 20, 24
+    R, S = k
+    ph, pw = (R - 1) // 2, (S - 1) // 2
+    x = rng.standard_normal((1, C, H, W)).astype(np.float32)
+    m = spatial.conv_spatial(rank, 1, 4, C, K, k, stride=stride, padding=(ph, pw), halo_len=0, bias=True).cuda()
+    w = m.weight.detach().cpu().numpy()
+    b = m.bias.detach().cpu().numpy()
+    top, bottom, left, right = m._inner_sides
+    xp = np.pad(x, ((0, 0), (0, 0), (0 if top else ph, 0 if bottom else ph), (0 if left else pw, 0 if right else pw)))
+    ref = so.conv2d_fwd(xp, w, b, (stride, stride))
+    xt = gu.t(x, grad=True)
+    if stride > 1 and (top or left):
+        with pytest.raises(NotImplementedError):
+            m(xt)
+        return
+    y = m(xt)
+    assert tuple(y.shape) == ref.shape, (y.shape, ref.shape)
+    _close(y.detach().cpu().numpy(), ref, _tol(ref, C, R, S), "fused y")
+    gy = rng.standard_normal(ref.shape).astype(np.float32)
+    y.backward(gu.t(gy))
+    dxp, dw, db = so.conv2d_bwd(xp, w, gy, (stride, stride))
+    Hp, Wp = xp.shape[2:]
+    dx_ref = dxp[:, :, (0 if top else ph):Hp - (0 if bottom else ph), (0 if left else pw):Wp - (0 if right else pw)]
+    _close(xt.grad.cpu().numpy(), dx_ref, _tol(dx_ref, K, R, S), "fused dx")
+    _close(m.weight.grad.cpu().numpy(), dw, 1e-4 * max(1.0, np.abs(dw).max()), "fused dw")

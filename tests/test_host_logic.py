@@ -62,6 +62,19 @@ def test_reference_assertions():
         spatial.conv_spatial(0, 1, 4, 3, 8, 3, padding=1, halo_len=1)
 
 
+def test_fused_halo_variant_border_sides():
+    """conv_spatial(halo_len=0): padding only on true image borders (reference table spatial.py:76-104
+    for the 2x2 grid: rank0 pads left/top, rank1 right/top, rank2 left/bottom, rank3 right/bottom)."""
+    inner = {r: spatial.conv_spatial(r, 1, 4, 3, 8, 3, padding=1, halo_len=0)._inner_sides for r in range(4)}
+    # (top, bottom, left, right) sides that face a neighbour
+    assert inner[0] == (False, True, False, True)
+    assert inner[1] == (False, True, True, False)
+    assert inner[2] == (True, False, False, True)
+    assert inner[3] == (True, False, True, False)
+    m = spatial.conv_spatial(0, 1, 4, 3, 8, 3, padding=1, halo_len=0)
+    assert m.neighbours is None   # never exchanges
+
+
 def test_no_cpu_fallback():
     m = spatial.conv_spatial(0, 1, 1, 3, 4, 3, padding=1)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
