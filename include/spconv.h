@@ -77,6 +77,16 @@ int spc_conv2d_fwd(const spc_conv_desc* d, const void* x, const spc_halo* halo, 
                    const void* bias, void* y, void* workspace, size_t workspace_bytes,
                    void* stream);
 
+/* The same convolution in two stream-ordered halves, so that the halo exchange (on a second
+ * stream) overlaps the bulk of the compute -- the design the reference left as dead code
+ * (spatial.py:415-866 make_tensor_halo_compute / compute_halo_exchange / merge_final_image):
+ *   interior: the whole tile with ZERO padding (no halo needed; tcgen05 where the shape qualifies);
+ *   boundary: recompute the output rows/cols whose window reaches a received strip. */
+int spc_conv2d_fwd_interior(const spc_conv_desc* d, const void* x, const void* w, const void* bias,
+                            void* y, void* workspace, size_t workspace_bytes, void* stream);
+int spc_conv2d_fwd_boundary(const spc_conv_desc* d, const void* x, const spc_halo* halo,
+                            const void* w, const void* bias, void* y, void* stream);
+
 /* dx = crop(dgrad(dy, w)) -- autograd of spatial.py:1027 followed by ZeroPad2d backward.
  * Reference semantics: received halos are constants, so no gradient is sent
  * back to neighbours; dx gets only this tile's own dy contributions.  dx: [N][C][H][W]. */
@@ -136,6 +146,18 @@ int   spc_mailbox_export(spc_mailbox* mb, unsigned char handle[SPC_IPC_HANDLE_BY
 /* Map a peer's mailbox (handle obtained from the peer through torch.distributed). */
 int   spc_mailbox_open(spc_mailbox** out, const unsigned char handle[SPC_IPC_HANDLE_BYTES],
                        size_t bytes, int nflags);
+/* Fused protocol steps (one kernel each).  post: wait until local ack flags ack_idx[d] reach
+ * ack_seq (0 = do not wait) -> pack every strip d with send[d] != NULL into send[d] (peer slot) ->
+ * when the whole grid is done, publish `seq` on peers[d]'s arrival flag arrival_idx[d].
+ * collect: wait for local arrival flags arrival_idx[d] >= seq -> copy bytes[d] from src[d] (local
+ * mailbox slot) to dst[d] -> publish `seq` on peers[d]'s ack flag ack_idx[d]. */
+int spc_halo_post(int N, int C, int H, int W, int halo_h, int halo_w, int dtype, const void* x,
+                  void* const send[9], spc_mailbox* self, spc_mailbox* const peers[9],
+                  const int ack_idx[9], uint32_t ack_seq, const int arrival_idx[9], uint32_t seq,
+                  void* stream);
+int spc_halo_collect(void* const dst[9], const void* const src[9], const size_t bytes[9],
+                     spc_mailbox* self, spc_mailbox* const peers[9], const int arrival_idx[9],
+                     uint32_t seq, const int ack_idx[9], void* stream);
 /* After writes to peer `mb` enqueued on `stream`: publish sequence number `seq` on flag `idx`. */
 int   spc_mailbox_signal(spc_mailbox* peer_mb, int idx, uint32_t seq, void* stream);
 /* Make `stream` wait (on device) until local flag `idx` reaches `seq`. */

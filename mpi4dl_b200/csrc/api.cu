@@ -77,25 +77,11 @@ size_t spc_conv_workspace_bytes(const spc_conv_desc* d, int op) {
   return spc_conv_uses_tcgen05(d, op) ? tc_workspace_bytes(d, op) : 0;
 }
 
-int spc_conv2d_fwd(const spc_conv_desc* d, const void* x, const spc_halo* halo, const void* w, const void* bias,
-                   void* y, void* workspace, size_t workspace_bytes, void* stream) {
-  int rc = validate(d);
-  if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (d->N == 0) return SPC_OK;
-  SPC_REQUIRE(x && w && y, "conv_fwd: null tensor pointer");
-  DirectConvParams p = fwd_params(d, x, halo, w, bias, y);
-  const bool tc = spc_conv_uses_tcgen05(d, 0);
-  if (d->algo == SPC_ALGO_TCGEN05 && !tc) {
-    set_error("conv_fwd: SPC_ALGO_TCGEN05 requested but the shape is not supported by the tcgen05 path");
-    return SPC_EUNSUPPORTED;
-  }
-  if (!tc) return launch_conv_direct(p, d->dtype, st);
-
-  rc = tc_conv_fwd(d, x, w, bias, y, workspace, workspace_bytes, st);
-  if (rc) return rc;
+// Boundary strips: output rows / columns whose window reaches outside the tile, recomputed from
+// tile + received halo strips (direct kernel).  Valid after ANY interior pass that used zero padding.
+static int fwd_boundary(const spc_conv_desc* d, DirectConvParams p, const spc_halo* halo, cudaStream_t st) {
   if (!has_halo(halo)) return SPC_OK;
-  // Boundary strips: output rows/cols whose window reaches outside the tile.
+  int rc;
   const int Ho = p.Ho, Wo = p.Wo;
   const int top = min(Ho, ceil_div(d->pad_h, d->stride_h));
   int bot0 = ceil_div(d->H + d->pad_h - d->R + 1, d->stride_h);  // first row touching the bottom halo
@@ -113,6 +99,49 @@ int spc_conv2d_fwd(const spc_conv_desc* d, const void* x, const spc_halo* halo, 
   if (any_left && (rc = fwd_rect(p, d->dtype, sy0, sy1, 0, left, st))) return rc;
   if (any_right && (rc = fwd_rect(p, d->dtype, sy0, sy1, right0, Wo, st))) return rc;
   return SPC_OK;
+}
+
+static int fwd_interior(const spc_conv_desc* d, const void* x, const void* w, const void* bias, void* y, void* workspace,
+                        size_t workspace_bytes, cudaStream_t st) {
+  const bool tc = spc_conv_uses_tcgen05(d, 0);
+  if (d->algo == SPC_ALGO_TCGEN05 && !tc) {
+    set_error("conv_fwd: SPC_ALGO_TCGEN05 requested but the shape is not supported by the tcgen05 path");
+    return SPC_EUNSUPPORTED;
+  }
+  if (tc) return tc_conv_fwd(d, x, w, bias, y, workspace, workspace_bytes, st);
+  return launch_conv_direct(fwd_params(d, x, nullptr, w, bias, y), d->dtype, st);
+}
+
+int spc_conv2d_fwd(const spc_conv_desc* d, const void* x, const spc_halo* halo, const void* w, const void* bias,
+                   void* y, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->N == 0) return SPC_OK;
+  SPC_REQUIRE(x && w && y, "conv_fwd: null tensor pointer");
+  if (!spc_conv_uses_tcgen05(d, 0) && d->algo != SPC_ALGO_TCGEN05)   // direct kernel reads tile + strips in one pass
+    return launch_conv_direct(fwd_params(d, x, halo, w, bias, y), d->dtype, st);
+  rc = fwd_interior(d, x, w, bias, y, workspace, workspace_bytes, st);
+  if (rc) return rc;
+  return fwd_boundary(d, fwd_params(d, x, halo, w, bias, y), halo, st);
+}
+
+int spc_conv2d_fwd_interior(const spc_conv_desc* d, const void* x, const void* w, const void* bias, void* y,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (d->N == 0) return SPC_OK;
+  SPC_REQUIRE(x && w && y, "conv_fwd_interior: null tensor pointer");
+  return fwd_interior(d, x, w, bias, y, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int spc_conv2d_fwd_boundary(const spc_conv_desc* d, const void* x, const spc_halo* halo, const void* w,
+                            const void* bias, void* y, void* stream) {
+  int rc = validate(d);
+  if (rc) return rc;
+  if (d->N == 0) return SPC_OK;
+  SPC_REQUIRE(x && w && y, "conv_fwd_boundary: null tensor pointer");
+  return fwd_boundary(d, fwd_params(d, x, halo, w, bias, y), halo, (cudaStream_t)stream);
 }
 
 int spc_conv2d_dgrad(const spc_conv_desc* d, const void* dy, const void* w, void* dx, void* workspace,

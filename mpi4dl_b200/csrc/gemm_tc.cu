@@ -308,7 +308,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int SMEM_LIMIT = 222 * 1024;   // leave room for a small co-resident kernel (halo post/collect, boundary strips)
 constexpr int SMEM_AUX = 1024 /*align*/ + 512 /*barriers*/;
 
 template <int MB>

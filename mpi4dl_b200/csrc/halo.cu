@@ -95,6 +95,93 @@ __global__ void mailbox_wait_kernel(const uint32_t* flag, uint32_t seq) {
   } while (true);
 }
 
+// ---- fused protocol kernels -----------------------------------------------------------------
+// post:    wait until every neighbour has drained the slot we are about to overwrite (ack flags,
+//          local memory) -> pack all strips straight into the neighbours' slots (peer stores) ->
+//          the LAST block publishes the sequence number on the neighbours' arrival flags.
+// collect: wait for the neighbours' arrival flags -> copy the received strips out of the mailbox
+//          into private buffers (they are needed again by wgrad) -> the last block acks.
+struct FlagSet {
+  uint32_t* wait[9];     // flags to wait on (>= wait_seq), NULL = skip
+  uint32_t* signal[9];   // flags to publish `seq` on when the whole grid is done, NULL = skip
+  uint32_t wait_seq, seq;
+  unsigned int* counter; // grid completion counter (device memory, self-resetting)
+};
+
+__device__ __forceinline__ void wait_flags(const FlagSet& f) {
+  if (threadIdx.x < 9) {
+    const uint32_t* w = f.wait[threadIdx.x];
+    if (w != nullptr) {
+      uint32_t v;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
+        if ((int32_t)(v - f.wait_seq) >= 0) break;
+        __nanosleep(32);
+      } while (true);
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void signal_when_grid_done(const FlagSet& f) {
+  __threadfence_system();          // this thread's (peer) stores are visible system-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(f.counter, 1u);
+    if (done == gridDim.x - 1) {   // every block has fenced its stores
+      __threadfence_system();
+      for (int i = 0; i < 9; ++i)
+        if (f.signal[i]) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.signal[i]), "r"(f.seq) : "memory");
+      *f.counter = 0u;
+    }
+  }
+}
+
+template <typename T>
+__global__ void halo_post_kernel(const PackParams p, const FlagSet f) {
+  wait_flags(f);
+  const long long total = p.off[9];
+  const T* x = reinterpret_cast<const T*>(p.x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int d = 0;
+#pragma unroll
+    for (int q = 1; q < 9; ++q) d += (i >= p.off[q]) ? 1 : 0;
+    const long long e = i - p.off[d];
+    const int dr = d / 3, dc = d % 3;
+    const int sh = (dr == 1) ? p.H : p.hh;
+    const int sw = (dc == 1) ? p.W : p.hw;
+    const int xw = (int)(e % sw);
+    const int yh = (int)((e / sw) % sh);
+    const long long nc = e / ((long long)sw * sh);
+    const int h = (dr == 0) ? yh : (dr == 2 ? p.H - p.hh + yh : yh);
+    const int w = (dc == 0) ? xw : (dc == 2 ? p.W - p.hw + xw : xw);
+    reinterpret_cast<T*>(p.send[d])[e] = x[(nc * p.H + h) * p.W + w];
+  }
+  signal_when_grid_done(f);
+}
+
+struct CollectParams {
+  const uint8_t* src[9];
+  uint8_t* dst[9];
+  long long off[10];   // prefix sums of byte counts (multiples of 2)
+};
+
+__global__ void halo_collect_kernel(const CollectParams p, const FlagSet f) {
+  wait_flags(f);
+  const long long total = p.off[9] / 2;   // 2-byte units (strips of bf16 columns may be 2-byte sized)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i * 2;
+    int d = 0;
+#pragma unroll
+    for (int q = 1; q < 9; ++q) d += (b >= p.off[q]) ? 1 : 0;
+    const long long e = b - p.off[d];
+    *reinterpret_cast<uint16_t*>(p.dst[d] + e) = *reinterpret_cast<const volatile uint16_t*>(p.src[d] + e);
+  }
+  signal_when_grid_done(f);
+}
+
 inline int grid_for(size_t total) {
   size_t b = (total + 255) / 256;
   if (b > 148 * 16) b = 148 * 16;
@@ -185,6 +272,68 @@ int spc_halo_crop(int N, int C, int H, int W, int halo_h, int halo_w, int dtype,
   return SPC_OK;
 }
 
+static uint32_t* mb_flag(spc_mailbox* mb, int idx);
+
+int spc_halo_post(int N, int C, int H, int W, int halo_h, int halo_w, int dtype, const void* x, void* const send[9],
+                  spc_mailbox* self, spc_mailbox* const peers[9], const int ack_idx[9], uint32_t ack_seq,
+                  const int arrival_idx[9], uint32_t seq, void* stream) {
+  SPC_REQUIRE(x && send && self && peers && ack_idx && arrival_idx, "halo_post: null pointer");
+  spc::PackParams p{};
+  p.x = x; p.N = N; p.C = C; p.H = H; p.W = W; p.hh = halo_h; p.hw = halo_w;
+  spc::FlagSet f{};
+  long long off = 0;
+  for (int d = 0; d < 9; ++d) {
+    p.off[d] = off;
+    p.send[d] = (d == 4) ? nullptr : send[d];
+    if (p.send[d]) {
+      SPC_REQUIRE(peers[d] != nullptr, "halo_post: no peer mailbox for direction %d", d);
+      const long long sh = (d / 3 == 1) ? H : halo_h, sw = (d % 3 == 1) ? W : halo_w;
+      off += (long long)N * C * sh * sw;
+      f.wait[d] = ack_seq ? mb_flag(self, ack_idx[d]) : nullptr;
+      f.signal[d] = mb_flag(peers[d], arrival_idx[d]);
+    }
+  }
+  p.off[9] = off;
+  if (off == 0) return SPC_OK;
+  f.wait_seq = ack_seq; f.seq = seq;
+  f.counter = reinterpret_cast<unsigned int*>(mb_flag(self, self->nflags));   // spare word after the flags
+  const int grid = spc::grid_for(off) > 64 ? 64 : spc::grid_for(off);
+  if (dtype == SPC_BF16) spc::halo_post_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(p, f);
+  else spc::halo_post_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(p, f);
+  spc::count_launch();
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
+int spc_halo_collect(void* const dst[9], const void* const src[9], const size_t bytes[9], spc_mailbox* self,
+                     spc_mailbox* const peers[9], const int arrival_idx[9], uint32_t seq, const int ack_idx[9],
+                     void* stream) {
+  SPC_REQUIRE(dst && src && bytes && self && peers, "halo_collect: null pointer");
+  spc::CollectParams p{};
+  spc::FlagSet f{};
+  long long off = 0;
+  for (int d = 0; d < 9; ++d) {
+    p.off[d] = off;
+    if (d != 4 && dst[d] && bytes[d]) {
+      SPC_REQUIRE(peers[d] != nullptr && src[d] != nullptr, "halo_collect: missing source for direction %d", d);
+      p.dst[d] = reinterpret_cast<uint8_t*>(dst[d]);
+      p.src[d] = reinterpret_cast<const uint8_t*>(src[d]);
+      off += (long long)bytes[d];
+      f.wait[d] = mb_flag(self, arrival_idx[d]);
+      f.signal[d] = mb_flag(peers[d], ack_idx[d]);
+    }
+  }
+  p.off[9] = off;
+  if (off == 0) return SPC_OK;
+  f.wait_seq = seq; f.seq = seq;
+  f.counter = reinterpret_cast<unsigned int*>(mb_flag(self, self->nflags + 1));
+  const int grid = spc::grid_for((size_t)off / 2) > 64 ? 64 : spc::grid_for((size_t)off / 2);
+  spc::halo_collect_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, f);
+  spc::count_launch();
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
 // ---- mailbox ---------------------------------------------------------------------------------
 static size_t mb_round(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -234,7 +383,7 @@ int spc_mailbox_open(spc_mailbox** out, const unsigned char handle[SPC_IPC_HANDL
   return SPC_OK;
 }
 
-static uint32_t* mb_flag(spc_mailbox* mb, int idx) {
+static uint32_t* mb_flag(spc_mailbox* mb, int idx) {   // idx may be nflags / nflags+1: two spare counter words
   return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(mb->base) + mb->bytes) + idx;
 }
 

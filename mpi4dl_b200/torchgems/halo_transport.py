@@ -150,6 +150,8 @@ class PeerTransport:
         return slots[key]
 
     def exchange(self, layer, x, hh, hw, mask, ranks):
+        """Two kernels per exchange: spc_halo_post (wait acks -> pack into the neighbours' slots ->
+        signal) and spc_halo_collect (wait arrivals -> copy the strips out -> ack)."""
         L = _lib.lib()
         st = _stream()
         slot = self._slot(layer, x, hh, hw)
@@ -157,31 +159,31 @@ class PeerTransport:
         seq = slot["seq"]
         par = seq & 1
         dirs = [i for i in range(9) if i != 4 and mask[i]]
-        arrival = lambda d: slot["flags"] + par * 9 + d
-        ack = lambda d: slot["flags"] + 18 + par * 9 + d
+        fb = slot["flags"]
         base_off = slot["data"] + par * slot["slot_bytes"]
-        ptrs = [0] * 9
-        for d in dirs:
-            pmb, pbase = self._peer(ranks[d])
-            if seq > 2:  # the neighbour must have drained what I wrote into this parity slot
-                _lib.check(L.spc_mailbox_wait(self.mb, ack(d), seq - 2, st), "spc_mailbox_wait(ack)")
-            ptrs[d] = pbase + base_off + slot["offs"][8 - d]
-        _pack(x, hh, hw, ptrs)
-        for d in dirs:
-            _lib.check(L.spc_mailbox_signal(self.peers[ranks[d]][0], arrival(8 - d), seq, st), "spc_mailbox_signal")
         N, Cc, H, W = x.shape
+        P9, I9, S9 = C.c_void_p * 9, C.c_int * 9, C.c_size_t * 9
+        send, peers, src, dst, nbytes = P9(), P9(), P9(), P9(), S9()
+        ack_local, arr_peer, arr_local, ack_peer = I9(), I9(), I9(), I9()
         recv = [None] * 9
         for d in dirs:
-            _lib.check(L.spc_mailbox_wait(self.mb, arrival(d), seq, st), "spc_mailbox_wait")
-        for d in dirs:
+            pmb, pbase = self._peer(ranks[d])
+            peers[d] = pmb
+            send[d] = pbase + base_off + slot["offs"][8 - d]      # my strip d is the neighbour's strip 8-d
+            ack_local[d] = fb + 18 + par * 9 + d                   # neighbour acks what I wrote (my flag)
+            arr_peer[d] = fb + par * 9 + (8 - d)                   # I announce it on the neighbour's flag
+            arr_local[d] = fb + par * 9 + d                        # neighbour announces my strip d here
+            ack_peer[d] = fb + 18 + par * 9 + (8 - d)              # and I ack on its flag
             shp = strip_shape(d, N, Cc, H, W, hh, hw)
-            n = x.element_size()
-            for s in shp:
-                n *= s
-            o = base_off + slot["offs"][d]
-            recv[d] = self.arena[o:o + n].view(x.dtype).view(shp).clone()  # private copy, then ack
-        for d in dirs:
-            _lib.check(L.spc_mailbox_signal(self.peers[ranks[d]][0], ack(8 - d), seq, st), "spc_mailbox_signal(ack)")
+            recv[d] = torch.empty(shp, dtype=x.dtype, device=x.device)
+            dst[d] = recv[d].data_ptr()
+            src[d] = self.base + base_off + slot["offs"][d]
+            nbytes[d] = recv[d].numel() * recv[d].element_size()
+        _lib.check(L.spc_halo_post(N, Cc, H, W, hh, hw, _lib.dtype_code(x.dtype), C.c_void_p(x.data_ptr()), C.byref(send),
+                                   self.mb, C.byref(peers), C.byref(ack_local), seq - 2 if seq > 2 else 0,
+                                   C.byref(arr_peer), seq, st), "spc_halo_post")
+        _lib.check(L.spc_halo_collect(C.byref(dst), C.byref(src), C.byref(nbytes), self.mb, C.byref(peers),
+                                      C.byref(arr_local), seq, C.byref(ack_peer), st), "spc_halo_collect")
         return recv
 
 
@@ -194,6 +196,11 @@ def get_transport(device):
         kind = os.environ.get("SPCONV_HALO_TRANSPORT", "peer" if device.type == "cuda" else "dist")
         _transport = PeerTransport(device) if kind == "peer" else DistTransport()
     return _transport
+
+
+def overlap_enabled():
+    """Overlap the exchange (comm stream) with the interior pass; SPCONV_HALO_OVERLAP=0 serialises."""
+    return os.environ.get("SPCONV_HALO_OVERLAP", "1") != "0"
 
 
 def set_transport(t):

@@ -150,6 +150,17 @@ def _strip_shape(i, N, Cc, H, W, hh, hw):
     return (N, Cc, H if dr == 0 else hh, W if dc == 0 else hw)
 
 
+_comm_streams = {}
+
+
+def _comm_stream(device):
+    """High-priority side stream for the halo exchange (one per device)."""
+    key = (device.type, device.index)
+    if key not in _comm_streams:
+        _comm_streams[key] = torch.cuda.Stream(device=device, priority=-1)
+    return _comm_streams[key]
+
+
 class _ConvSpatialFn(torch.autograd.Function):
     """fprop / dgrad / wgrad through the C ABI.  Halo strips enter as constants: the reference
     unpacks them with in-place slice assignment of detached tensors, so no gradient ever flows
@@ -157,15 +168,28 @@ class _ConvSpatialFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, desc_args, *strips):
+        """strips[0:9] are the received halo strips; an optional 10th element is a CUDA event that
+        fires when they have arrived (exchange running on the comm stream): then the interior pass
+        is launched first and only the boundary strips wait for the event."""
         L = _lib.lib()
         d = _lib.ConvDesc(*desc_args)
+        ctx.n_tail = len(strips)
+        ready = strips[9] if len(strips) > 9 else None
+        strips = strips[:9]
         Ho, Wo = C.c_int(), C.c_int()
         L.spc_conv_out_shape(C.byref(d), C.byref(Ho), C.byref(Wo))
         y = torch.empty((d.N, d.K, Ho.value, Wo.value), dtype=x.dtype, device=x.device)
         halo = _lib.make_halo(strips)
         ws, wsp = _workspace(L.spc_conv_workspace_bytes(C.byref(d), 0), x.device)
-        _lib.check(L.spc_conv2d_fwd(C.byref(d), _ptr(x), C.byref(halo), _ptr(weight), _ptr(bias), _ptr(y), wsp,
-                                    0 if ws is None else ws.numel(), _stream()), "spc_conv2d_fwd")
+        if ready is None:
+            _lib.check(L.spc_conv2d_fwd(C.byref(d), _ptr(x), C.byref(halo), _ptr(weight), _ptr(bias), _ptr(y), wsp,
+                                        0 if ws is None else ws.numel(), _stream()), "spc_conv2d_fwd")
+        else:
+            _lib.check(L.spc_conv2d_fwd_interior(C.byref(d), _ptr(x), _ptr(weight), _ptr(bias), _ptr(y), wsp,
+                                                 0 if ws is None else ws.numel(), _stream()), "spc_conv2d_fwd_interior")
+            torch.cuda.current_stream().wait_event(ready)
+            _lib.check(L.spc_conv2d_fwd_boundary(C.byref(d), _ptr(x), C.byref(halo), _ptr(weight), _ptr(bias), _ptr(y),
+                                                 _stream()), "spc_conv2d_fwd_boundary")
         ctx.desc_args = desc_args
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight, *[s for s in strips if s is not None])
@@ -196,7 +220,7 @@ class _ConvSpatialFn(torch.autograd.Function):
                                           wsp, 0 if ws is None else ws.numel(), _stream()), "spc_conv2d_wgrad")
             dw = dw32.to(weight.dtype)
             db = db32.to(weight.dtype) if db32 is not None else None
-        return (dx, dw, db, None) + (None,) * 9
+        return (dx, dw, db, None) + (None,) * ctx.n_tail
 
 
 class conv_spatial(nn.Conv2d, _SpatialTopology):
@@ -271,12 +295,29 @@ class conv_spatial(nn.Conv2d, _SpatialTopology):
         if x.dtype != self.weight.dtype:
             raise RuntimeError("conv_spatial: input dtype %s != weight dtype %s" % (x.dtype, self.weight.dtype))
         hh, hw = self.halo_len_height, self.halo_len_width
-        with torch.no_grad():
-            strips = self._exchange(x, hh, hw) if ((hh > 0 or hw > 0) and not self.fused_halo) else [None] * 9
         N, Cc, H, W = x.shape
         desc_args = (N, Cc, H, W, self.out_channels, self.kernel_size[0], self.kernel_size[1], self.stride[0],
                      self.stride[1], hh, hw, _lib.dtype_code(x.dtype), self.algo)
-        y = _ConvSpatialFn.apply(x, self.weight, self.bias, desc_args, *strips)
+        exchange = (hh > 0 or hw > 0) and not self.fused_halo and self.neighbours is not None and any(self.neighbours)
+        extra = ()
+        with torch.no_grad():
+            if exchange and halo_transport.overlap_enabled():
+                # exchange on the comm stream, overlapped with the interior pass on this stream
+                main = torch.cuda.current_stream()
+                comm = _comm_stream(x.device)
+                comm.wait_stream(main)                     # x is complete
+                with torch.cuda.stream(comm):
+                    strips = self._exchange(x, hh, hw)
+                    ready = torch.cuda.Event()
+                    ready.record(comm)
+                x.record_stream(comm)
+                for t in strips:
+                    if t is not None:
+                        t.record_stream(main)
+                extra = (ready,)
+            else:
+                strips = self._exchange(x, hh, hw) if exchange else [None] * 9
+        y = _ConvSpatialFn.apply(x, self.weight, self.bias, desc_args, *strips, *extra)
         if self.fused_halo:
             y = self._crop_fused(y, H, W)
         return y
