@@ -45,6 +45,66 @@ DirectConvParams fwd_params(const spc_conv_desc* d, const void* x, const spc_hal
   return p;
 }
 
+inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// Boundary rect through the tcgen05 path: gather a 64-column-aligned patch of tile+halo around the
+// rect, run the SAME fast convolution on that small image, scatter the rect back.  Stride 1 only.
+static bool patch_ok(const spc_conv_desc* d, int op) {
+  if (d->dtype != SPC_BF16 || d->stride_h != 1 || d->stride_w != 1 || d->algo == SPC_ALGO_DIRECT) return false;
+  spc_conv_desc q = *d;
+  q.H = 64; q.W = 64; q.N = d->N;
+  return tc_supported(&q, op);
+}
+
+static int patch_fwd_rect(const spc_conv_desc* d, const void* x, const spc_halo* halo, const void* w, const void* bias,
+                          void* y, int y0, int y1, int x0, int x1, cudaStream_t st) {
+  if (y1 <= y0 || x1 <= x0) return SPC_OK;
+  const int rh = y1 - y0, rw = x1 - x0, ph = d->pad_h, pw = d->pad_w;
+  spc_conv_desc q = *d;
+  q.H = rh + 2 * ph;
+  q.W = ((rw + 2 * pw) + 63) & ~63;
+  q.algo = SPC_ALGO_TCGEN05;
+  const size_t esz = dtype_size(d->dtype);
+  const size_t pbytes = al256((size_t)d->N * d->C * q.H * q.W * esz), obytes = al256((size_t)d->N * d->K * q.H * q.W * esz);
+  const size_t wsb = tc_workspace_bytes(&q, 0);
+  char* base = (char*)boundary_scratch(pbytes + obytes + wsb + 1024);
+  SPC_REQUIRE(base != nullptr, "boundary scratch allocation failed");
+  void* P = base; void* O = base + pbytes; void* ws = base + pbytes + obytes;
+  TileView v = make_view(x, halo, d->N, d->C, d->H, d->W, ph, pw);
+  int rc = launch_patch_gather(v, P, q.H, q.W, y0 - ph, x0 - pw, d->dtype, st);
+  if (rc) return rc;
+  rc = tc_conv_fwd(&q, P, w, bias, O, ws, wsb, st);
+  if (rc) return rc;
+  int Ho, Wo;
+  spc_conv_out_shape(d, &Ho, &Wo);
+  return launch_patch_scatter(O, y, d->N * d->K, Ho, Wo, q.H, q.W, y0, x0, rh, rw, ph, pw, d->dtype, st);
+}
+
+// dw += (halo pixels only) x (dy restricted to the rect), through the tcgen05 wgrad on a patch
+static int patch_wgrad_rect(const spc_conv_desc* d, const spc_halo* halo, const void* dy, float* dw, int y0, int y1,
+                            int x0, int x1, cudaStream_t st) {
+  if (y1 <= y0 || x1 <= x0) return SPC_OK;
+  const int rh = y1 - y0, rw = x1 - x0, ph = d->pad_h, pw = d->pad_w;
+  spc_conv_desc q = *d;
+  q.H = rh + 2 * ph;
+  q.W = ((rw + 2 * pw) + 63) & ~63;
+  q.algo = SPC_ALGO_TCGEN05;
+  const size_t esz = dtype_size(d->dtype);
+  const size_t pbytes = al256((size_t)d->N * d->C * q.H * q.W * esz), gbytes = al256((size_t)d->N * d->K * q.H * q.W * esz);
+  const size_t wsb = tc_workspace_bytes(&q, 2);
+  char* base = (char*)boundary_scratch(pbytes + gbytes + wsb + 1024);
+  SPC_REQUIRE(base != nullptr, "boundary scratch allocation failed");
+  void* P = base; void* G = base + pbytes; void* ws = base + pbytes + gbytes;
+  TileView v = make_view(nullptr, halo, d->N, d->C, d->H, d->W, ph, pw);   // halo pixels only
+  int rc = launch_patch_gather(v, P, q.H, q.W, y0 - ph, x0 - pw, d->dtype, st);
+  if (rc) return rc;
+  int Ho, Wo;
+  spc_conv_out_shape(d, &Ho, &Wo);
+  rc = launch_patch_gather_dy(dy, G, d->N * d->K, Ho, Wo, q.H, q.W, y0, x0, rh, rw, ph, pw, d->dtype, st);
+  if (rc) return rc;
+  return tc_conv_wgrad(&q, P, G, dw, 1, ws, wsb, st);
+}
+
 // Launch the direct kernel on the output sub-rectangle [y0,y1) x [x0,x1).
 int fwd_rect(DirectConvParams p, int dtype, int y0, int y1, int x0, int x1, cudaStream_t st) {
   if (y1 <= y0 || x1 <= x0) return SPC_OK;
@@ -93,9 +153,17 @@ static int fwd_boundary(const spc_conv_desc* d, DirectConvParams p, const spc_ha
   const bool any_bot = halo->strip[6] || halo->strip[7] || halo->strip[8];
   const bool any_left = halo->strip[0] || halo->strip[3] || halo->strip[6];
   const bool any_right = halo->strip[2] || halo->strip[5] || halo->strip[8];
+  const int sy0 = any_top ? top : 0, sy1 = any_bot ? bot0 : Ho;   // rows not already redone by the bands
+  if (patch_ok(d, 0)) {
+    const void* x = p.in.x; const void* w = p.w; const void* bias = p.bias; void* y = p.y;
+    if (any_top && (rc = patch_fwd_rect(d, x, halo, w, bias, y, 0, top, 0, Wo, st))) return rc;
+    if (any_bot && (rc = patch_fwd_rect(d, x, halo, w, bias, y, bot0, Ho, 0, Wo, st))) return rc;
+    if (any_left && (rc = patch_fwd_rect(d, x, halo, w, bias, y, sy0, sy1, 0, left, st))) return rc;
+    if (any_right && (rc = patch_fwd_rect(d, x, halo, w, bias, y, sy0, sy1, right0, Wo, st))) return rc;
+    return SPC_OK;
+  }
   if (any_top && (rc = fwd_rect(p, d->dtype, 0, top, 0, Wo, st))) return rc;
   if (any_bot && (rc = fwd_rect(p, d->dtype, bot0, Ho, 0, Wo, st))) return rc;
-  const int sy0 = any_top ? top : 0, sy1 = any_bot ? bot0 : Ho;   // rows not already redone above
   if (any_left && (rc = fwd_rect(p, d->dtype, sy0, sy1, 0, left, st))) return rc;
   if (any_right && (rc = fwd_rect(p, d->dtype, sy0, sy1, right0, Wo, st))) return rc;
   return SPC_OK;
@@ -227,9 +295,23 @@ int spc_conv2d_wgrad(const spc_conv_desc* d, const void* x, const spc_halo* halo
       // add the halo pixels' contribution: the direct kernel over a view that holds ONLY the
       // strips (interior reads as zero) -- exact by linearity -- restricted to the output strips
       // whose windows reach outside the tile.
-      p.in = make_view(nullptr, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);
-      rc = launch_wgrad_halo(p, d->dtype, st);
-      if (rc) return rc;
+      if (patch_ok(d, 2)) {
+        const int top = min(Ho, d->pad_h), bot0 = max(top, min(Ho, d->H + d->pad_h - d->R + 1));
+        const int left = min(Wo, d->pad_w), right0 = max(left, min(Wo, d->W + d->pad_w - d->S + 1));
+        const bool any_top = halo->strip[0] || halo->strip[1] || halo->strip[2];
+        const bool any_bot = halo->strip[6] || halo->strip[7] || halo->strip[8];
+        const bool any_left = halo->strip[0] || halo->strip[3] || halo->strip[6];
+        const bool any_right = halo->strip[2] || halo->strip[5] || halo->strip[8];
+        const int sy0 = any_top ? top : 0, sy1 = any_bot ? bot0 : Ho;
+        if (any_top && (rc = patch_wgrad_rect(d, halo, dy, dw, 0, top, 0, Wo, st))) return rc;
+        if (any_bot && (rc = patch_wgrad_rect(d, halo, dy, dw, bot0, Ho, 0, Wo, st))) return rc;
+        if (any_left && (rc = patch_wgrad_rect(d, halo, dy, dw, sy0, sy1, 0, left, st))) return rc;
+        if (any_right && (rc = patch_wgrad_rect(d, halo, dy, dw, sy0, sy1, right0, Wo, st))) return rc;
+      } else {
+        p.in = make_view(nullptr, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);
+        rc = launch_wgrad_halo(p, d->dtype, st);
+        if (rc) return rc;
+      }
     }
   } else {
     p.in = make_view(x, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);

@@ -68,6 +68,28 @@ __device__ __forceinline__ float tile_load(const TileView& v, int n, int c, int 
   return to_f32<T>(s[(((size_t)n * v.C + c) * sh + y) * sw + xx]);
 }
 
+// Address of element (n,c,h,w) of the tile-or-halo view, or nullptr where the view reads as zero.
+// Splitting the address computation from the load lets callers batch several independent loads.
+template <typename T>
+__device__ __forceinline__ const T* tile_ptr(const TileView& v, int n, int c, int h, int w) {
+  const bool hin = (unsigned)h < (unsigned)v.H;
+  const bool win = (unsigned)w < (unsigned)v.W;
+  if (hin && win) {
+    if (v.x == nullptr) return nullptr;
+    return reinterpret_cast<const T*>(v.x) + (((size_t)n * v.C + c) * v.H + h) * v.W + w;
+  }
+  const int dr = h < 0 ? 0 : (hin ? 1 : 2);
+  const int dc = w < 0 ? 0 : (win ? 1 : 2);
+  const T* s = reinterpret_cast<const T*>(v.strip[dr * 3 + dc]);
+  if (s == nullptr) return nullptr;
+  const int sh = (dr == 1) ? v.H : v.hh;
+  const int sw = (dc == 1) ? v.W : v.hw;
+  const int y = (dr == 0) ? h + v.hh : (dr == 2 ? h - v.H : h);
+  const int xx = (dc == 0) ? w + v.hw : (dc == 2 ? w - v.W : w);
+  if ((unsigned)y >= (unsigned)sh || (unsigned)xx >= (unsigned)sw) return nullptr;
+  return s + (((size_t)n * v.C + c) * sh + y) * sw + xx;
+}
+
 inline TileView make_view(const void* x, const spc_halo* halo, int N, int C, int H, int W, int hh, int hw) {
   TileView v;
   v.x = x;
@@ -109,6 +131,14 @@ int launch_wgrad_direct(const DirectWgradParams& p, int dtype, cudaStream_t st);
 // dw += contribution of the halo pixels only (boundary output pixels x taps that fall outside the tile)
 int launch_wgrad_halo(const DirectWgradParams& p, int dtype, cudaStream_t st);
 int launch_bias_grad(const void* dy, float* db, int N, int K, int HW, int dtype, int accumulate, cudaStream_t st);
+
+// ---- boundary patches (halo.cu) ---------------------------------------------------------------
+void* boundary_scratch(size_t bytes);
+int launch_patch_gather(const TileView& v, void* P, int Hp, int Wp, int h0, int w0, int dtype, cudaStream_t st);
+int launch_patch_gather_dy(const void* dy, void* G, int NK, int Ho, int Wo, int Hp, int Wp, int y0, int x0, int rh, int rw,
+                           int ph, int pw, int dtype, cudaStream_t st);
+int launch_patch_scatter(const void* O, void* y, int NK, int Ho, int Wo, int Hp, int Wp, int y0, int x0, int rh, int rw,
+                         int ph, int pw, int dtype, cudaStream_t st);
 
 // ---- tcgen05 pointwise GEMM path: gemm_tc.cu ---------------------------------------------
 bool tc_supported(const spc_conv_desc* d, int op);

@@ -56,14 +56,30 @@ conv_direct_kernel(const DirectConvParams p, const int CB, const int tiles_x, co
   for (int c0 = 0; c0 < C; c0 += CB) {
     __syncthreads();
     const int patch_elems = CB * PH * PW;
-    for (int i = threadIdx.x; i < patch_elems; i += DC_THREADS) {
-      const int pw = i % PW;
-      const int t = i / PW;
-      const int ph = t % PH;
-      const int c = t / PH;
-      float v = 0.f;
-      if (c0 + c < C) v = tile_load<T>(p.in, n, c0 + c, h_base + ph, w_base + pw);
-      patch[(c * PH + ph) * PWp + pw] = v;
+    // four independent global loads in flight per thread (addresses first, then loads, then smem stores)
+    for (int i0 = threadIdx.x; i0 < patch_elems; i0 += 4 * DC_THREADS) {
+      const T* ptr[4];
+      int dst[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * DC_THREADS;
+        ptr[u] = nullptr;
+        dst[u] = -1;
+        if (i < patch_elems) {
+          const int pw = i % PW;
+          const int t = i / PW;
+          const int ph = t % PH;
+          const int c = t / PH;
+          dst[u] = (c * PH + ph) * PWp + pw;
+          if (c0 + c < C) ptr[u] = tile_ptr<T>(p.in, n, c0 + c, h_base + ph, w_base + pw);
+        }
+      }
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ptr[u] ? to_f32<T>(__ldg(ptr[u])) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (dst[u] >= 0) patch[dst[u]] = v[u];
     }
     const int w_elems = CB * RS * DC_KB;
     for (int i = threadIdx.x; i < w_elems; i += DC_THREADS) {
@@ -315,7 +331,10 @@ wgrad_halo_kernel(const DirectWgradParams p, const int kblocks, const int npix, 
               g = active ? to_f32<T>(dy[(((size_t)n * p.K + k) * p.Ho + oy) * p.Wo + ox]) : 0.f;
               loaded = true;
             }
-            if (active) acc[u] = fmaf(g, tile_load<T>(p.in, n, c, h, w), acc[u]);
+            if (active) {
+              const T* ptr = tile_ptr<T>(p.in, n, c, h, w);
+              if (ptr) acc[u] = fmaf(g, to_f32<T>(__ldg(ptr)), acc[u]);
+            }
           }
           if (++sx == p.S) { sx = 0; ++r; }
         }
