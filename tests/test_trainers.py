@@ -11,7 +11,10 @@ import torch.multiprocessing as mp
 import torch.nn as nn
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "trainer_golden.json")))["cases"]
+_G = json.load(open(os.path.join(ROOT, "tests", "golden", "trainer_golden.json")))
+GOLD = _G["cases"]
+SP_GOLD = _G["sp_cases"]
+IMG, IMG_SEQ = 16, 8
 
 
 def build_model():
@@ -65,6 +68,100 @@ def test_lp_trainer_matches_reference_losses(idx, name):
         assert p.exitcode == 0
     assert got[0][1] == GOLD[name]["shape_list"]
     assert got[case["world"] - 1][0] == pytest.approx(GOLD[name]["losses"], rel=1e-6, abs=1e-6)
+
+
+def build_sp_model(img):
+    torch.manual_seed(4321)
+    return nn.Sequential(
+        nn.Conv2d(3, 8, 1), nn.ReLU(), nn.Conv2d(8, 8, 1), nn.ReLU(),
+        nn.Conv2d(8, 4, 3, stride=2, padding=1), nn.Flatten(), nn.Linear(4 * (img // 2) ** 2, 10))
+
+
+def _sp_world(case):
+    return case["P"] * case["spatial_size"] + case["split"] - case["spatial_size"]
+
+
+def _sp_worker(rank, case, port, q):
+    import sys
+    from types import SimpleNamespace
+    sys.path.insert(0, ROOT)
+    world = _sp_world(case)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      CUDA_VISIBLE_DEVICES="")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from mpi4dl_b200.torchgems.mp_pipeline import model_generator
+    from mpi4dl_b200.torchgems.train_spatial import get_shapes_spatial, split_input, train_model_spatial
+    P, S = case["P"], case["spatial_size"]
+    nsp_list = [P] * S
+    nsp = P if S == 1 else nsp_list
+    local_rank = world - 1 - rank if case["inverse"] else rank
+    split_rank = local_rank // P if local_rank < P * S else local_rank - P * S + S
+    mb = case["batch"] // case["parts"]
+    seq = model_generator(model=build_sp_model(IMG_SEQ), split_size=case["split"], input_size=(mb, 3, IMG_SEQ, IMG_SEQ),
+                          balance=case["balance"])
+    seq.ready_model(split_rank=split_rank, GET_SHAPES_ON_CUDA=False)
+    shapes = get_shapes_spatial(seq.shape_list, case["slice"], S, nsp_list, IMG // IMG_SEQ)
+    gen = model_generator(model=build_sp_model(IMG), split_size=case["split"], input_size=(mb, 3, IMG, IMG),
+                          balance=case["balance"], shape_list=shapes)
+    gen.ready_model(split_rank=split_rank)
+    tm = train_model_spatial(gen, local_rank, case["batch"], epochs=1, spatial_size=S, num_spatial_parts=nsp,
+                             parts=case["parts"], ASYNC=True, GEMS_INVERSE=case["inverse"], slice_method=case["slice"],
+                             mpi_comm=SimpleNamespace(mp_size=world))
+    losses = []
+    for step in range(3):
+        g = torch.Generator().manual_seed(200 + step)
+        x = torch.randn(case["batch"], 3, IMG, IMG, generator=g)
+        y = torch.randint(0, 10, (case["batch"],), generator=g)
+        if local_rank < P:
+            x = split_input(x, IMG, case["slice"], local_rank, nsp_list)
+        loss, _ = tm.run_step(x, y)
+        tm.update()
+        losses.append(float(loss))
+    q.put((local_rank, losses, [list(s) if not isinstance(s, list) else [list(t) for t in s] for s in shapes]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("idx,name", list(enumerate(sorted(SP_GOLD))))
+def test_sp_trainer_matches_reference_losses(idx, name):
+    """SP+LP trainer (tiles -> join rank -> tail), incl. two spatial stages, square/strip slicing,
+    micro-batches and the mirrored (GEMS inverse) rank line, against the reference's own losses."""
+    case = SP_GOLD[name]["case"]
+    world = _sp_world(case)
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    ps = [ctx.Process(target=_sp_worker, args=(r, case, 29890 + idx, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    got = {r: (l, s) for r, l, s in (q.get() for _ in ps)}
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    assert got[0][1] == SP_GOLD[name]["shape_list"]
+    assert got[world - 1][0] == pytest.approx(SP_GOLD[name]["losses"], rel=1e-6, abs=1e-6)
+
+
+def test_spatial_config_helpers():
+    from mpi4dl_b200.torchgems.train_spatial import get_shapes_spatial, split_input, verify_spatial_config
+    verify_spatial_config("square", 8192, [4])
+    verify_spatial_config("vertical", 1024, [8, 8])
+    for bad in (("diagonal", 1024, [4]), ("square", 1000, [4]), ("vertical", 1024, [3]), ("vertical", 1024, [4, 2])):
+        with pytest.raises(AssertionError):
+            verify_spatial_config(*bad)
+    shapes = [(2, 8, 32, 32), [(2, 8, 16, 16), (2, 4, 16, 16)], (2, 16, 8, 8), (2, 10)]
+    assert get_shapes_spatial(shapes, "square", 2, [4, 4], 4) == \
+        [(2, 8, 64, 64), [(2, 8, 32, 32), (2, 4, 32, 32)], (2, 16, 32, 32), (2, 10)]
+    assert get_shapes_spatial(shapes, "vertical", 1, [4], 2) == \
+        [(2, 8, 64, 16), [(2, 8, 32, 32), (2, 4, 32, 32)], (2, 16, 16, 16), (2, 10)]
+    assert get_shapes_spatial(shapes, "horizontal", 2, [2, 2], 1)[:2] == [(2, 8, 16, 32), [(2, 8, 8, 16), (2, 4, 8, 16)]]
+    x = torch.arange(2 * 1 * 8 * 8).reshape(2, 1, 8, 8)
+    assert torch.equal(split_input(x, 8, "square", 3, [4]), x[:, :, 4:, 4:])
+    assert torch.equal(split_input(x, 8, "square", 1, [4]), x[:, :, :4, 4:])
+    assert torch.equal(split_input(x, 8, "vertical", 1, [4]), x[:, :, :, 2:4])
+    assert torch.equal(split_input(x, 8, "horizontal", 3, [4]), x[:, :, 6:, :])
+    # odd tile counts: the last strip takes the remainder (train_spatial.py:268-276)
+    assert split_input(x, 8, "vertical", 2, [3]).shape[-1] == 4
 
 
 def test_parser_namespace_matches_reference():
