@@ -122,6 +122,8 @@ class train_model:
         self.GEMS_INVERSE = GEMS_INVERSE
         self.batch_size = batch_size
         self.device = _device()
+        # activations travel in the model's dtype (fp32 as in the reference; bf16 when the model was cast)
+        self.dtype = next((p.dtype for p in self.models.parameters() if p.is_floating_point()), torch.float32)
         # subclasses (train_model_spatial) set these before calling us
         if not hasattr(self, "num_spatial_parts"):
             self.num_spatial_parts = 1
@@ -154,8 +156,9 @@ class train_model:
 
     def _empty_like_shapes(self, shapes, requires_grad):
         if isinstance(shapes, list):
-            return tuple(torch.zeros(self._parts_shape(s), device=self.device, requires_grad=requires_grad) for s in shapes)
-        return torch.zeros(self._parts_shape(shapes), device=self.device, requires_grad=requires_grad)
+            return tuple(torch.zeros(self._parts_shape(s), device=self.device, dtype=self.dtype, requires_grad=requires_grad)
+                         for s in shapes)
+        return torch.zeros(self._parts_shape(shapes), device=self.device, dtype=self.dtype, requires_grad=requires_grad)
 
     def initialize_recv_buffers(self):
         """One activation buffer per micro-batch (their .grad is what travels back) and one buffer
@@ -173,13 +176,25 @@ class train_model:
     def _as_list(x):
         return list(x) if isinstance(x, (tuple, list)) else [x]
 
+    @staticmethod
+    def _host_staged(t):
+        """gloo cannot move CUDA tensors point-to-point: stage through the host (debug / single-GPU
+        test configuration only; NCCL sends device buffers directly)."""
+        return t.is_cuda and dist.get_backend() != "nccl"
+
     def _send(self, tensors, dst):
         for t in self._as_list(tensors):
-            dist.send(t.detach().contiguous(), dst=dst)
+            t = t.detach().contiguous()
+            dist.send(t.cpu() if self._host_staged(t) else t, dst=dst)
 
     def _recv(self, tensors, src):
         for t in self._as_list(tensors):
-            dist.recv(t, src=src)
+            if self._host_staged(t):
+                h = torch.empty(t.shape, dtype=t.dtype)
+                dist.recv(h, src=src)
+                t.copy_(h)
+            else:
+                dist.recv(t, src=src)
 
     # names kept from the reference; sync and async variants behave the same on stream-ordered backends
     def receive_input_sync(self, part_number):
@@ -214,7 +229,7 @@ class train_model:
         if self.split_rank != self.split_size - 1:
             self.send_input_async(y)
             return y, None
-        loss = self.criterion(y, data_y)
+        loss = self.criterion(y.float(), data_y)          # no-op for fp32 models
         corrects = (data_y.eq(torch.argmax(y, dim=-1).long())).sum().float()
         return loss, corrects / self.batch_size
 
@@ -235,8 +250,10 @@ class train_model:
 
     def run_step(self, data_x, data_y):
         """GPipe-style fill/drain: all micro-batch forwards, then all backwards (:509-534)."""
-        data_x = data_x.to(self.device)
-        data_y = data_y.to(self.device)
+        data_x = data_x.to(self.device, non_blocking=True)
+        data_y = data_y.to(self.device, non_blocking=True)
+        if data_x.is_floating_point() and data_x.dtype != self.dtype:
+            data_x = data_x.to(self.dtype)
         per = int(self.batch_size / self.parts)
         outs, loss, corrects = [], 0, 0
         for i in range(self.parts):

@@ -160,13 +160,16 @@ class train_model_spatial(train_model):
                              for _ in range(self.parts)]
 
     def receive_input_async_joint(self, part_number, ranks=None):
-        ops = []
+        """All P tiles (every tensor of each) in one batched receive."""
+        bufs = [t for buf in self.input_x_list[part_number] for t in self._as_list(buf)]
+        srcs = [src for buf, src in zip(self.input_x_list[part_number], self._tile_ranks()) for _ in self._as_list(buf)]
         with torch.no_grad():
-            for buf, src in zip(self.input_x_list[part_number], self._tile_ranks()):
-                for t in self._as_list(buf):
-                    ops.append(dist.P2POp(dist.irecv, t, src))
-            for w in dist.batch_isend_irecv(ops):
+            staged = [torch.empty(t.shape, dtype=t.dtype) if self._host_staged(t) else t for t in bufs]
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.irecv, h, s) for h, s in zip(staged, srcs)]):
                 w.wait()
+            for t, h in zip(bufs, staged):
+                if h is not t:
+                    t.copy_(h)
 
     recv_inputs_joint = receive_input_async_joint
 
@@ -174,7 +177,8 @@ class train_model_spatial(train_model):
         ops = []
         for buf, dst in zip(input_x_list, self._tile_ranks()):
             for t in self._as_list(buf):
-                ops.append(dist.P2POp(dist.isend, t.grad.contiguous(), dst))
+                g = t.grad.contiguous()
+                ops.append(dist.P2POp(dist.isend, g.cpu() if self._host_staged(g) else g, dst))
         for w in dist.batch_isend_irecv(ops):
             w.wait()
 
@@ -220,7 +224,7 @@ class train_model_spatial(train_model):
             if self.split_rank != self.split_size - 1:
                 self.send_input_async(y)
                 return y, None
-            loss = self.criterion(y, data_y)
+            loss = self.criterion(y.float(), data_y)          # no-op for fp32 models
         corrects = (data_y.eq(torch.argmax(y, dim=-1).long())).sum().float()
         return loss, corrects / self.batch_size
 

@@ -1,0 +1,103 @@
+"""CPU-only: the model builders (mpi4dl_b200.models) produce the reference's module trees -- same
+state-dict keys and shapes, same placement of conv_spatial / Pool vs ordinary layers -- and the
+sequential builders compute the same function (fixtures from the UNMODIFIED reference:
+tools/gen_model_golden.py -> tests/golden/model_golden.json)."""
+import hashlib
+import json
+import os
+import warnings
+
+import pytest
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "model_golden.json")))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _pg():
+    """conv_spatial asks dist.get_rank() while it wires its neighbours."""
+    made = False
+    if not dist.is_initialized():
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29781")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+        made = True
+    yield
+    if made:
+        dist.destroy_process_group()
+
+
+def _sig(m):
+    return hashlib.sha256(repr([(k, tuple(v.shape)) for k, v in m.state_dict().items()]).encode()).hexdigest()
+
+
+def _kinds(m):
+    # (the reference's Pool wraps an inner nn pool named ".pool"; the generator skips those too)
+    ks = [(n, type(x).__name__) for n, x in m.named_modules()
+          if type(x).__name__ in ("Conv2d", "conv_spatial", "Pool")
+          or (type(x).__name__ in ("AvgPool2d", "MaxPool2d") and not n.endswith(".pool"))]
+    return hashlib.sha256(repr(ks).encode()).hexdigest(), sum(t == "conv_spatial" for _, t in ks), sum(t == "Pool" for _, t in ks)
+
+
+def _fill(m):
+    for i, (k, v) in enumerate(sorted(m.state_dict().items())):
+        g = torch.Generator().manual_seed(i)
+        if v.dtype.is_floating_point:
+            v.copy_(torch.rand(v.shape, generator=g) + 0.5 if "running_var" in k else torch.randn(v.shape, generator=g) * 0.1)
+
+
+def _check(m, e, fwd_size=None):
+    assert _sig(m) == e["state_sig"]
+    assert sum(p.numel() for p in m.parameters()) == e["params"]
+    kh, nconv, npool = _kinds(m)
+    assert (kh, nconv, npool) == (e["kinds_sig"], e["spatial_convs"], e["spatial_pools"])
+    if "forward" in e:
+        warnings.simplefilter("ignore")
+        _fill(m)
+        x = torch.randn(2, 3, fwd_size, fwd_size, generator=torch.Generator().manual_seed(77))
+        for mode in ("train", "eval"):
+            getattr(m, mode)()
+            with torch.no_grad():
+                y = m(x).double().flatten()
+            assert torch.allclose(y, torch.tensor(e["forward"][mode], dtype=torch.float64), rtol=1e-4, atol=1e-6), mode
+
+
+@pytest.mark.parametrize("e", GOLD["resnet"], ids=lambda e: "v%d_d%d" % (e["version"], e["depth"]))
+def test_resnet_sequential(e):
+    from mpi4dl_b200.models import resnet
+    _check(getattr(resnet, "get_resnet_v%d" % e["version"])((2, 3, 32, 32), e["depth"]), e, 32)
+
+
+@pytest.mark.parametrize("e", GOLD["resnet_spatial"], ids=lambda e: "v%d_d%d_%s" % (e["version"], e["depth"], e["kw"]["slice_method"]))
+def test_resnet_spatial_structure(e):
+    from mpi4dl_b200.models import resnet_spatial
+    _check(getattr(resnet_spatial, "get_resnet_v%d" % e["version"])((2, 3, 64, 64), e["depth"], **e["kw"]), e)
+
+
+@pytest.mark.parametrize("e", GOLD["amoebanet"], ids=lambda e: "L%d_F%d" % (e["num_layers"], e["num_filters"]))
+def test_amoebanet_sequential(e):
+    from mpi4dl_b200.models import amoebanet
+    _check(amoebanet.amoebanetd(num_classes=10, num_layers=e["num_layers"], num_filters=e["num_filters"]), e, 64)
+
+
+@pytest.mark.parametrize("e", GOLD["amoebanet_spatial"],
+                         ids=lambda e: "L%d_mp%d_%s" % (e["num_layers"], e["kw"]["mp_size"], "bal" if e["kw"]["balance"] else "even"))
+def test_amoebanet_spatial_structure(e):
+    from mpi4dl_b200.models import amoebanet
+    m = amoebanet.amoebanetd_spatial(local_rank=0, spatial_size=1, num_spatial_parts=4, slice_method="square", num_classes=10,
+                                     num_layers=e["num_layers"], num_filters=e["num_filters"], **e["kw"])
+    _check(m, e)
+
+
+def test_bench_workload_is_the_spatial_stage_of_amoebanetd():
+    """bench.py's layer list (tests/golden/layers_amoebanetd_sp4.json, traced from the reference)
+    is what amoebanetd_spatial(18, 416) builds for stage 0 at mp_size=4... same conv_spatial count."""
+    from mpi4dl_b200.models import amoebanet
+    m = amoebanet.amoebanetd_spatial(local_rank=0, spatial_size=1, num_spatial_parts=4, mp_size=2, slice_method="square",
+                                     num_classes=10, num_layers=18, num_filters=416)
+    layers = json.load(open(os.path.join(ROOT, "tests", "golden", "layers_amoebanetd_sp4.json")))
+    layers = layers["layers"] if isinstance(layers, dict) else layers
+    n_conv = sum(type(x).__name__ == "conv_spatial" for x in m.modules())
+    n_pool = sum(type(x).__name__ == "Pool" for x in m.modules())
+    assert n_conv >= sum(l["op"] == "conv" for l in layers) and n_pool >= sum(l["op"] == "pool" for l in layers)
