@@ -36,8 +36,8 @@ def _builders(kind, args, mb, image_size, spatial_kw):
         from mpi4dl_b200.models import resnet, resnet_spatial
         seq_size, depth = 32, get_depth(2, 12)
         seq = resnet.get_resnet_v2((mb, 3, seq_size, seq_size), depth=depth, num_classes=args.num_classes)
-        model = resnet_spatial.get_resnet_v2(input_shape=(mb, 3, image_size, image_size), depth=depth,
-                                             num_classes=args.num_classes, fused_layers=args.fused_layers, **spatial_kw)
+        model = resnet_spatial.get_resnet_v2(depth=depth, num_classes=args.num_classes, fused_layers=args.fused_layers,
+                                             **spatial_kw)
         return seq, seq_size, model
     from mpi4dl_b200.models import amoebanet
     seq_size = min(512, image_size)

@@ -37,7 +37,7 @@ def _batch(step):
 def _sequential_losses(width):
     m = nn.Sequential(*_layers(lambda ci, co, k, s: nn.Conv2d(ci, co, k, stride=s, padding=k // 2),
                                lambda: nn.AvgPool2d(3, stride=1, padding=1), width)).cuda()
-    opt = torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9)
+    opt = torch.optim.SGD(m.parameters(), lr=0.005, momentum=0.9)
     crit = nn.CrossEntropyLoss()
     n_spatial = sum(1 for _ in nn.Sequential(*list(m)[:BALANCE[0]]).parameters())
     losses = []
@@ -79,7 +79,7 @@ def _worker(rank, method, width, dtype, port, ngpu, q):
     shapes = get_shapes_spatial(full, method, 1, [P], 1)
     gen = model_generator(model=model, split_size=SPLIT, input_size=(BATCH, 3, IMG, IMG), balance=BALANCE, shape_list=shapes)
     gen.ready_model(split_rank=split_rank)
-    opt = torch.optim.SGD(gen.models.parameters(), lr=0.05, momentum=0.9)
+    opt = torch.optim.SGD(gen.models.parameters(), lr=0.005, momentum=0.9)
     tm = train_model_spatial(gen, local_rank, BATCH, epochs=1, spatial_size=1, num_spatial_parts=P, optimizer=opt,
                              parts=1, slice_method=method, mpi_comm=mpi_comm)
     sync.sync_model_spatial(gen)
@@ -94,7 +94,7 @@ def _worker(rank, method, width, dtype, port, ngpu, q):
         tm.update()
         losses.append(float(loss))
     from mpi4dl_b200 import _lib
-    q.put((local_rank, losses, int(_lib.lib().spc_launch_count())))
+    q.put((local_rank, losses, int(_lib.lib().spc_launch_count(0))))
     dist.barrier()
     dist.destroy_process_group()
 
