@@ -54,6 +54,10 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
     set_error("cuTensorMapEncodeTiled entry point not available");
     return SPC_ECUDA;
   }
+  if (cudaFree(nullptr) != cudaSuccess) {   // bind the primary context to this (possibly autograd worker) thread
+    set_error("tcgen05 conv: no CUDA context on this thread");
+    return SPC_ECUDA;
+  }
   cuuint64_t gd[5], gs[5];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) {
@@ -103,7 +107,7 @@ struct PwParams {
   int P;                       // pixels per image
   int N;                       // images
   int tiles_per_image;
-  int num_mg;                  // groups of 512 output channels (X tile re-read per group, from L2)
+  int num_mg;                  // groups of MB*128 output channels (X tile re-read per group, from L2)
   int num_tiles;               // N * tiles_per_image * num_mg
   int stages;                  // pipeline depth (runtime, <= MAX_STAGES)
   int wres;                    // 1: all weight chunks stay resident in smem (loaded once per CTA)
@@ -185,7 +189,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           if (!p.wres) {
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb)
-              tma_load_2d(st + mb * A_BLK_BYTES, &tmap_w, &full[s], kc * BK, tap * p.Mpad + mg * 512 + mb * 128);
+              tma_load_2d(st + mb * A_BLK_BYTES, &tmap_w, &full[s], kc * BK, tap * p.Mpad + mg * (MB * 128) + mb * 128);
             st += MB * A_BLK_BYTES;
           }
           if (p.taps == 1) {
@@ -260,7 +264,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       tc_fence_after();
 #pragma unroll 1
       for (int mb = 0; mb < MB; ++mb) {
-        const int k0 = mg * 512 + mb * 128;
+        const int k0 = mg * (MB * 128) + mb * 128;
         if (k0 >= p.M) break;                       // block-uniform: nothing valid in this block
         const int k = k0 + row;
         const float bias = (k < p.M && p.bias) ? __bfloat162float(p.bias[k]) : 0.f;
@@ -431,11 +435,19 @@ int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bi
     if (p.tgroup < 1) p.tgroup = 1;
   }
   const int MBtot = Mpad / 128;
-  p.num_mg = (Mpad + 511) / 512;
+  // 3+ blocks of output channels: two groups of 256 with double-buffered accumulators (the epilogue of
+  // one tile overlaps the K loop of the next) beat one group of 512 whose single accumulator set
+  // serialises them, even though the activation tile is then read once per group (from L2).
+  // Measured (r1, profiles/): wins for Cin <= 416 (+6..19 %), loses for Cin >= 624 where the K loop is
+  // long enough to hide the epilogue and the extra activation reads cost more than the overlap gains.
+  int mb = MBtot >= 3 ? (c.Cin <= 512 ? 2 : 4) : MBtot;
+  if (MBtot >= 3 && getenv("SPC_PW_MB4")) mb = 4;                 // A/B knobs
+  if (MBtot >= 3 && getenv("SPC_PW_MB2")) mb = 2;
+  p.num_mg = (MBtot + mb - 1) / mb;
   p.tiles_per_image = (P + BN - 1) / BN;
   p.num_tiles = p.tiles_per_image * c.N * p.num_mg;
-  if (MBtot == 1) return launch_pw<1>(tw, tx, tx4, ty, p, st);
-  if (MBtot == 2) return launch_pw<2>(tw, tx, tx4, ty, p, st);
+  if (mb == 1) return launch_pw<1>(tw, tx, tx4, ty, p, st);
+  if (mb == 2) return launch_pw<2>(tw, tx, tx4, ty, p, st);
   return launch_pw<4>(tw, tx, tx4, ty, p, st);
 }
 
@@ -468,6 +480,8 @@ struct WgParams {
   int TG, passes;   // taps per pass, ceil(taps / TG)
   int W, shiftN;    // OUTPUT image width; N if x is the S column-shifted copies, else 0
   int rowmul;       // input row = rowmul * output row + tap row offset
+  int split_major;  // 1: concurrently running CTAs cover all (m-group, channel-block, pass) groups of the SAME
+                    //    pixel range, so the dY / x chunks every group re-reads come from L2, not HBM
 };
 
 template <int MG>
@@ -497,13 +511,14 @@ pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int num_items = p.mgroups * p.n_blocks * p.passes * p.splits;
+  const int ngroups = p.mgroups * p.n_blocks * p.passes;
+  const int num_items = ngroups * p.splits;
   const int per_split = (p.chunks_total + p.splits - 1) / p.splits;
 
   // item -> (split, tap pass, channel block, m group)
 #define WG_DECODE(it)                                                        \
-  const int sp = (it) % p.splits;                                            \
-  const int g_ = (it) / p.splits;                                            \
+  const int sp = p.split_major ? (it) / ngroups : (it) % p.splits;           \
+  const int g_ = p.split_major ? (it) % ngroups : (it) / p.splits;           \
   const int pass = g_ % p.passes;                                            \
   const int nb = (g_ / p.passes) % p.n_blocks;                               \
   const int mgp = g_ / (p.passes * p.n_blocks);                              \
@@ -627,17 +642,32 @@ int launch_wg(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMap& 
   p.stages = (SMEM_LIMIT - SMEM_AUX) / stage_bytes;
   if (p.stages > 6) p.stages = 6;
   SPC_REQUIRE(p.stages >= 2, "tcgen05 wgrad: smem budget");
-  const int groups = p.mgroups * p.n_blocks * p.passes;
-  int splits = (2 * 148 + groups - 1) / groups;
-  if (splits > p.chunks_total / 8) splits = p.chunks_total / 8;
-  if (splits < 1) splits = 1;
-  p.splits = splits;
-  const int smem = p.stages * stage_bytes + SMEM_AUX;
-  auto kern = pw_wgrad_kernel<MG>;
-  SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int groups = p.mgroups * p.n_blocks * p.passes;
+  // items = groups * splits run on a persistent grid of `sms` CTAs: pick the split count whose item
+  // count fills whole waves (2 waves when possible).  Rounding UP here left a third, nearly empty
+  // wave for e.g. 14 groups x 22 splits = 308 items on 148 SMs (69 % efficiency).
+  int splits = 1;
+  {
+    double best = 0.0;
+    const int smax = (2 * sms) / groups > 1 ? (2 * sms) / groups : 1;
+    for (int s = 1; s <= smax; ++s) {          // at most two waves; efficiency = items / (waves * sms)
+      const int items_s = groups * s, waves = (items_s + sms - 1) / sms;
+      const double eff = (double)items_s / ((double)waves * sms);
+      if (eff > best + 1e-9) { best = eff; splits = s; }
+      else if (eff > best - 0.02 && waves == 2) { splits = s; if (eff > best) best = eff; }   // prefer two waves
+    }
+  }
+  if (getenv("SPC_WG_SPLIT_CEIL")) splits = (2 * sms + groups - 1) / groups;   // previous behaviour (A/B knob)
+  if (splits > p.chunks_total / 8) splits = p.chunks_total / 8;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  p.split_major = getenv("SPC_WG_GROUP_MAJOR") ? 0 : 1;            // A/B knob: previous item order
+  const int smem = p.stages * stage_bytes + SMEM_AUX;
+  auto kern = pw_wgrad_kernel<MG>;
+  SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
   const int items = groups * p.splits;
   kern<<<items < sms ? items : sms, TC_THREADS, smem, st>>>(tdy, tx, tx4, p);
   count_launch();

@@ -6,7 +6,10 @@
 // These ops are pure HBM streaming (AI ~ 0): one read of x, one write of y.
 #include <stdlib.h>
 
+#include <cuda.h>
+
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace spc {
 namespace {
@@ -344,6 +347,207 @@ pool3_s1_rolling_kernel(const PoolParams p) {
   }
 }
 
+// ---- forward, 3x3 stride 1, TMA-staged ----------------------------------------------------------
+// The rolling kernel above is latency/occupancy bound (1.8 TB/s): each warp keeps only a few
+// 16-byte loads in flight.  Here one producer thread per CTA keeps P3_STAGES bulk-tensor loads of
+// whole (64+2) x (16*VEC + 2*VEC) input boxes in flight; TMA's out-of-bounds zero fill IS the zero
+// padding, so the 256 consumer threads run a branch-free stencil out of shared memory (one 16-byte
+// vector per thread per row, neighbours by shuffle) and store 16 bytes per thread per output row.
+// The box starts VEC columns left of the tile so its inner coordinate stays 16-byte aligned.
+// Halos of a partitioned tile are not visible to TMA: callers re-do the 1-pixel output ring with
+// pool3_s1_ring_kernel when the view has strips.
+constexpr int P3_TH = 64;          // output rows per tile
+constexpr int P3_STAGES = 4;
+constexpr int P3_THREADS = 288;    // 8 consumer warps + 1 producer warp
+
+template <typename T> struct P3Geom {
+  static constexpr int VEC = 16 / sizeof(T);
+  static constexpr int TW = 16 * VEC;                 // output columns per tile (256 bytes per row)
+  static constexpr int BW = TW + 2 * VEC;             // box columns
+  static constexpr int BH = P3_TH + 2;                // box rows
+  static constexpr int BOX_BYTES = BW * BH * (int)sizeof(T);
+  static constexpr int STAGE_BYTES = (BOX_BYTES + 1023) & ~1023;
+  static constexpr int SMEM_BYTES = P3_STAGES * STAGE_BYTES + 1024 + 128;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(P3_THREADS, 2)
+pool3_s1_tma_kernel(const __grid_constant__ CUtensorMap tmap, const PoolParams p, int tiles_w, int tiles_h,
+                    int num_tiles) {
+  using G = P3Geom<T>;
+  constexpr int VEC = G::VEC;
+  extern __shared__ uint8_t p3_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p3_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + P3_STAGES * G::STAGE_BYTES);
+  uint64_t* empty = full + P3_STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P3_STAGES; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 8); }
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  const int per_plane = tiles_w * tiles_h;
+  if (warp == 8) {
+    if (lane == 0) {
+      tc::tma_prefetch_desc(&tmap);
+      int s = 0, ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int plane = t / per_plane, r = t - plane * per_plane;
+        const int h0 = (r / tiles_w) * P3_TH, w0 = (r % tiles_w) * G::TW;
+        tc::mbar_wait(&empty[s], ph ^ 1);
+        tc::mbar_arrive_expect_tx(&full[s], G::BOX_BYTES);
+        tc::tma_load_3d(smem + s * G::STAGE_BYTES, &tmap, &full[s], w0 - VEC, h0 - 1, plane);
+        if (++s == P3_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+  const int cg = threadIdx.x & 15;          // 16-byte column group inside the tile
+  const int rs = threadIdx.x >> 4;          // 4-row segment (0..15)
+  const bool is_max = p.mode == SPC_POOL_MAX;
+  const float inv = 1.f / 9.f;
+  T* out = reinterpret_cast<T*>(p.out);
+  int s = 0, ph = 0;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const int plane = t / per_plane, r = t - plane * per_plane;
+    const int h0 = (r / tiles_w) * P3_TH, w0 = (r % tiles_w) * G::TW;
+    tc::mbar_wait(&full[s], ph);
+    const T* sm = reinterpret_cast<const T*>(smem + s * G::STAGE_BYTES) + (rs * 4) * G::BW + VEC + cg * VEC;
+    const int wq = w0 + cg * VEC;
+    float h0v[VEC], h1v[VEC], h2v[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) { h0v[q] = 0.f; h1v[q] = 0.f; h2v[q] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {           // box rows rs*4 + k = input rows h0 + rs*4 + k - 1
+      const uint4 cur = *reinterpret_cast<const uint4*>(sm + k * G::BW);
+      const T* e = reinterpret_cast<const T*>(&cur);
+      float body[VEC];
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) body[q] = to_f32<T>(e[q]);
+      float left = __shfl_up_sync(0xffffffffu, body[VEC - 1], 1, 16);
+      float right = __shfl_down_sync(0xffffffffu, body[0], 1, 16);
+      if (cg == 0) left = to_f32<T>(sm[k * G::BW - 1]);
+      if (cg == 15) right = to_f32<T>(sm[k * G::BW + VEC]);
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        h0v[q] = h1v[q];
+        h1v[q] = h2v[q];
+        const float a = q == 0 ? left : body[q - 1];
+        const float b = q == VEC - 1 ? right : body[q + 1];
+        h2v[q] = is_max ? fmaxf(fmaxf(a, body[q]), b) : (a + body[q] + b);
+      }
+      if (k >= 2) {
+        const int h = h0 + rs * 4 + k - 2;
+        if (h < p.in.H && wq < p.in.W) {
+          float outv[VEC];
+#pragma unroll
+          for (int q = 0; q < VEC; ++q)
+            outv[q] = is_max ? fmaxf(fmaxf(h0v[q], h1v[q]), h2v[q]) : (h0v[q] + h1v[q] + h2v[q]) * inv;
+          store_vec<T, VEC>(out + ((size_t)plane * p.in.H + h) * p.in.W + wq, outv);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&empty[s]);
+    if (++s == P3_STAGES) { s = 0; ph ^= 1; }
+  }
+}
+
+// 1-pixel output ring of a 3x3 stride-1 pool, through the tile + halo view
+template <typename T>
+__global__ void pool3_s1_ring_kernel(const PoolParams p) {
+  const int H = p.in.H, W = p.in.W;
+  const int ring = (H >= 2 ? 2 * W : W) + (H > 2 ? 2 * (H - 2) : 0);
+  const size_t total = (size_t)p.in.N * p.in.C * ring;
+  const bool is_max = p.mode == SPC_POOL_MAX;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i % ring);
+    const size_t nc = i / ring;
+    const int c = (int)(nc % p.in.C), n = (int)(nc / p.in.C);
+    int h, w;
+    if (r < W) { h = 0; w = r; }
+    else if (H >= 2 && r < 2 * W) { h = H - 1; w = r - W; }
+    else { const int q = r - 2 * W; h = 1 + (q >> 1); w = (q & 1) ? W - 1 : 0; }
+    float acc = is_max ? -INFINITY : 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const float v = tile_load<T>(p.in, n, c, h + dy, w + dx);
+        acc = is_max ? fmaxf(acc, v) : acc + v;
+      }
+    reinterpret_cast<T*>(p.out)[(nc * H + h) * (size_t)W + w] = from_f32<T>(is_max ? acc : acc * (1.f / 9.f));
+  }
+}
+
+typedef CUresult (*P3EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// x viewed as [planes][H][W]; returns SPC_OK and launches, or a negative value when TMA cannot be used
+template <typename T>
+int launch_pool3_tma(const PoolParams& p, cudaStream_t st) {
+  using G = P3Geom<T>;
+  static P3EncodeFn enc = nullptr;
+  if (!enc) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled entry point not available");
+      return SPC_ECUDA;
+    }
+    enc = reinterpret_cast<P3EncodeFn>(fp);
+  }
+  // the driver-API encode needs a current context on THIS thread; a backward pass can be the first
+  // CUDA work of an autograd worker thread, which the runtime binds only at its first runtime call
+  SPC_CHECK_CUDA(cudaFree(nullptr));
+  const size_t planes = (size_t)p.in.N * p.in.C;
+  CUtensorMap tm;
+  const cuuint64_t gd[3] = {(cuuint64_t)p.in.W, (cuuint64_t)p.in.H, (cuuint64_t)planes};
+  const cuuint64_t gs[2] = {(cuuint64_t)p.in.W * sizeof(T), (cuuint64_t)p.in.W * p.in.H * sizeof(T)};
+  const cuuint32_t bx[3] = {(cuuint32_t)G::BW, (cuuint32_t)G::BH, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  const CUresult r = enc(&tm, sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                         const_cast<void*>(p.in.x), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("pool: cuTensorMapEncodeTiled failed (%d) W=%d H=%d planes=%zu", (int)r, p.in.W, p.in.H, planes);
+    return SPC_ECUDA;
+  }
+  const int tiles_w = (p.in.W + G::TW - 1) / G::TW, tiles_h = (p.in.H + P3_TH - 1) / P3_TH;
+  const size_t nt = planes * tiles_w * tiles_h;
+  SPC_REQUIRE(nt < (1u << 31), "pool: too many tiles");
+  auto kern = pool3_s1_tma_kernel<T>;
+  SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = nt < (size_t)(2 * sms) ? (int)nt : 2 * sms;
+  kern<<<grid, P3_THREADS, G::SMEM_BYTES, st>>>(tm, p, tiles_w, tiles_h, (int)nt);
+  count_launch();
+  SPC_CHECK_CUDA(cudaGetLastError());
+  bool halos = false;
+  for (int i = 0; i < 9; ++i) halos = halos || p.in.strip[i] != nullptr;
+  if (halos) {
+    const int ring = 2 * p.in.W + 2 * p.in.H;
+    const size_t total = planes * ring;
+    const int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+    pool3_s1_ring_kernel<T><<<blocks, 256, 0, st>>>(p);
+    count_launch();
+    SPC_CHECK_CUDA(cudaGetLastError());
+  }
+  return SPC_OK;
+}
+
+// TMA needs: 16-byte aligned base and row pitch, planes*H*W addressable by the 3-D map
+template <typename T>
+bool pool3_tma_ok(const PoolParams& p) {
+  return getenv("SPC_POOL_NOTMA") == nullptr && p.in.x != nullptr && (uintptr_t)p.in.x % 16 == 0 &&
+         ((size_t)p.in.W * sizeof(T)) % 16 == 0 && p.in.H >= 1 && p.in.W >= 1;
+}
+
 // ---- backward: one thread per dx element (gather over the windows that cover it) -------------
 template <typename T>
 __global__ void pool_bwd_kernel(const PoolParams p) {
@@ -475,7 +679,9 @@ int run_fwd(const PoolParams& p, cudaStream_t st) {
                       p.in.W == p.Wo * p.stride;
   const size_t vtotal = total / VEC;
   const int blocks = (int)((vtotal + 255) / 256 > 148 * 32 ? 148 * 32 : (vtotal + 255) / 256);
-  if (vec_ok && p.k == 3 && p.stride == 1 && p.in.W % (VEC * 32) != 0) {
+  if (vec_ok && p.k == 3 && p.stride == 1 && pool3_tma_ok<T>(p)) {
+    return launch_pool3_tma<T>(p, st);
+  } else if (vec_ok && p.k == 3 && p.stride == 1 && p.in.W % (VEC * 32) != 0) {
     pool3_fwd_kernel<T, VEC, 1><<<blocks, 256, 0, st>>>(p);
   } else if (vec_ok && p.k == 3 && p.stride == 1 && getenv("SPC_POOL_SIMPLE") != nullptr) {
     pool3_s1_simple_kernel<T, VEC><<<blocks, 256, 0, st>>>(p);
@@ -515,6 +721,7 @@ int run_bwd(const PoolParams& p, cudaStream_t st) {
     const size_t items = (size_t)q.in.N * q.in.C * ((q.in.H + RB - 1) / RB) * (q.in.W / VEC);
     const int b2 = (int)((items + 255) / 256 > 148 * 16 ? 148 * 16 : (items + 255) / 256);
     const int b1 = (int)((vt + 255) / 256 > 148 * 32 ? 148 * 32 : (vt + 255) / 256);
+    if (pool3_tma_ok<T>(q)) return launch_pool3_tma<T>(q, st);
     if (getenv("SPC_POOL_SIMPLE") != nullptr) pool3_s1_simple_kernel<T, VEC><<<b1, 256, 0, st>>>(q);
     else if (q.in.W % (VEC * 32) == 0) pool3_s1_rolling_kernel<T, VEC, RB><<<b2, 256, 0, st>>>(q);
     else pool3_fwd_kernel<T, VEC, 1><<<b1, 256, 0, st>>>(q);

@@ -22,4 +22,13 @@ for (Cc, K, R, S, H, W) in shapes:
         _lib.check(L.spc_conv2d_dgrad(C.byref(d), gy.data_ptr(), w.data_ptr(), dx.data_ptr(), ws.data_ptr(), nb, sp()), "dgrad")
         _lib.check(L.spc_conv2d_wgrad(C.byref(d), x.data_ptr(), None, gy.data_ptr(), dw.data_ptr(), None, 0, ws.data_ptr(), nb, sp()), "wgrad")
     torch.cuda.synchronize()
+# 3x3 stride-1 average pool (TMA-staged kernel), forward and backward, at the AmoebaNet cell shape
+x = torch.randn(1, 416, 1024, 1024, device=dev).to(torch.bfloat16)
+y = torch.empty_like(x)
+dx = torch.empty_like(x)
+pd = _lib.PoolDesc(1, 416, 1024, 1024, 3, 1, 1, _lib.SPC_POOL_AVG, _lib.SPC_BF16)
+for _ in range(2):
+    _lib.check(L.spc_pool2d_fwd(C.byref(pd), x.data_ptr(), None, y.data_ptr(), sp()), "pool fwd")
+    _lib.check(L.spc_pool2d_bwd(C.byref(pd), x.data_ptr(), None, y.data_ptr(), dx.data_ptr(), sp()), "pool bwd")
+torch.cuda.synchronize()
 print("done")
