@@ -117,8 +117,10 @@ def conv_bytes_flops(l, tile_h, tile_w, esz):
 def pool_bytes(l, tile_h, tile_w, esz):
     Ho = (tile_h + 2 * l["pad"] - l["k"]) // l["stride"] + 1
     Wo = (tile_w + 2 * l["pad"] - l["k"]) // l["stride"] + 1
-    return dict(fwd=((l["C"] * tile_h * tile_w + l["C"] * Ho * Wo) * esz, 0.0),
-                bwd=((l["C"] * tile_h * tile_w * 2 + l["C"] * Ho * Wo) * esz, 0.0))
+    xin, yout = l["C"] * tile_h * tile_w, l["C"] * Ho * Wo
+    # backward: read dy, write dx; only max pooling also has to re-read x (to find the arg-max)
+    return dict(fwd=((xin + yout) * esz, 0.0),
+                bwd=((xin + yout + (xin if l["mode"] == "max" else 0)) * esz, 0.0))
 
 
 # ------------------------------------------------------------------------------------------------

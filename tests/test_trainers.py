@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _G = json.load(open(os.path.join(ROOT, "tests", "golden", "trainer_golden.json")))
 GOLD = _G["cases"]
 SP_GOLD = _G["sp_cases"]
+GEMS_GOLD = _G["gems_cases"]
 IMG, IMG_SEQ = 16, 8
 
 
@@ -140,6 +141,57 @@ def test_sp_trainer_matches_reference_losses(idx, name):
         assert p.exitcode == 0
     assert got[0][1] == SP_GOLD[name]["shape_list"]
     assert got[world - 1][0] == pytest.approx(SP_GOLD[name]["losses"], rel=1e-6, abs=1e-6)
+
+
+def _gems_worker(rank, case, port, q, zero_init):
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    os.environ["SPCONV_GEMS_REFERENCE_ZERO_INIT"] = "1" if zero_init else "0"
+    import gems_cases
+    gems_cases.worker(rank, case, port, q, "ours")
+
+
+def _run_gems(case, port, zero_init):
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    ps = [ctx.Process(target=_gems_worker, args=(r, case, port, q, zero_init)) for r in range(case["world"])]
+    for p in ps:
+        p.start()
+    got = dict(q.get() for _ in ps)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    return got
+
+
+@pytest.mark.parametrize("idx,name", list(enumerate(sorted(GEMS_GOLD))))
+def test_gems_master_trainers_match_reference_losses(idx, name):
+    """GEMS master (two mirrored replicas) on LP and on SP+LP: per-rank loss sequences of the
+    reference.  The SP variant runs with the reference's zero-initialised flat parameter buffers
+    (see train_spatial_master._flatten) to compare like with like."""
+    case = GEMS_GOLD[name]["case"]
+    got = _run_gems(case, 29900 + idx, zero_init=True)
+    for r, want in GEMS_GOLD[name]["losses"].items():
+        assert got[int(r)] == pytest.approx(want, rel=1e-6, abs=1e-6), r
+
+
+def test_gems_sp_master_keeps_initial_parameters_by_default():
+    """Default (non-reference) behaviour: flattening keeps the initial weights, so the two replicas
+    start from their own initialisation and the first loss is not ln(10)."""
+    case = GEMS_GOLD["gems_sp2_vertical"]["case"]
+    got = _run_gems(case, 29910, zero_init=False)
+    import math
+    first = got[3][0]
+    assert abs(first - math.log(10)) > 1e-3 and math.isfinite(first)
+
+
+def test_spatial_master_config():
+    from mpi4dl_b200.torchgems.train_spatial_master import verify_spatial_master_config
+    verify_spatial_master_config("square", 1024, [4], 1, 8)
+    with pytest.raises(AssertionError):
+        verify_spatial_master_config("square", 1024, [4], 1, 5)     # replica tiles would share GPUs
 
 
 def test_spatial_config_helpers():

@@ -93,6 +93,15 @@ def sp_worker(rank, case, port, q):
     dist.destroy_process_group()
 
 
+def gems_worker(rank, case, port, q):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.join(HERE, "..", "tests"))
+    import ref_shim
+    ref_shim.install()
+    import gems_cases
+    gems_cases.worker(rank, case, port, q, "reference")
+
+
 def worker(rank, case, port, q):
     sys.path.insert(0, HERE)
     import ref_shim
@@ -146,9 +155,25 @@ def main():
         sp[case["name"]] = dict(case=case, losses=got[world - 1][0], shape_list=got[0][1])
         print(case["name"], got[world - 1][0], flush=True)
     res_sp = sp
+    sys.path.insert(0, os.path.join(HERE, "..", "tests"))
+    import gems_cases
+    res_gems = {}
+    for case in gems_cases.GEMS_CASES:
+        port += 1
+        q = ctx.SimpleQueue()
+        ps = [ctx.Process(target=gems_worker, args=(r, case, port, q)) for r in range(case["world"])]
+        for p in ps:
+            p.start()
+        got = dict(q.get() for _ in ps)
+        for p in ps:
+            p.join()
+        res_gems[case["name"]] = dict(case=case, losses={str(r): l for r, l in sorted(got.items())})
+        print(case["name"], got, flush=True)
     json.dump({"source": "tools/gen_trainer_golden.py on unmodified /root/reference mp_pipeline.py (gloo, CPU)", "cases": res,
                "sp_source": "same script, unmodified /root/reference train_spatial.py (train_model_spatial, get_shapes_spatial, split_input)",
-               "sp_cases": res_sp},
+               "sp_cases": res_sp,
+               "gems_source": "tests/gems_cases.py worker on unmodified /root/reference gems_master.py / train_spatial_master.py",
+               "gems_cases": res_gems},
               open(OUT, "w"), indent=1)
 
 
