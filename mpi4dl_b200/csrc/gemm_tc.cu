@@ -480,6 +480,8 @@ struct WgParams {
   int TG, passes;   // taps per pass, ceil(taps / TG)
   int W, shiftN;    // OUTPUT image width; N if x is the S column-shifted copies, else 0
   int rowmul;       // input row = rowmul * output row + tap row offset
+  int mrows;        // dY rows per 128-lane block (<= 128): K split EVENLY over its blocks, so every item streams the
+                    // same number of valid rows and the CTAs that share an x chunk stay in lock-step (L2 hits)
   int split_major;  // 1: concurrently running CTAs cover all (m-group, channel-block, pass) groups of the SAME
                     //    pixel range, so the dY / x chunks every group re-reads come from L2, not HBM
 };
@@ -538,9 +540,10 @@ pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
           const int n = ch / p.chunks_per_image, p0 = (ch % p.chunks_per_image) * 64;
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * stage_bytes;
-          mbar_arrive_expect_tx(&full[s], MG * A_BLK_BYTES + ntap * b_bytes);
+          mbar_arrive_expect_tx(&full[s], MG * p.mrows * 128 + ntap * b_bytes);
 #pragma unroll
-          for (int i = 0; i < MG; ++i) tma_load_3d(st + i * A_BLK_BYTES, &tmap_dy, &full[s], p0, (mgp * MG + i) * 128, n);
+          for (int i = 0; i < MG; ++i)
+            tma_load_3d(st + i * A_BLK_BYTES, &tmap_dy, &full[s], p0, (mgp * MG + i) * p.mrows, n);
           if (p.taps == 1) {
             tma_load_3d(st + MG * A_BLK_BYTES, &tmap_x, &full[s], p0, nb * p.nblk, n);
           } else {
@@ -599,7 +602,8 @@ pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         for (int t = 0; t < ntap; ++t) {
 #pragma unroll 1
           for (int i = 0; i < MG; ++i) {
-            const int k = (mgp * MG + i) * 128 + quarter * 32 + lane;
+            const int rib = quarter * 32 + lane;                     // row inside the block (= TMEM lane)
+            const int k = rib < p.mrows ? (mgp * MG + i) * p.mrows + rib : p.K;   // lanes >= mrows hold garbage
 #pragma unroll 1
             for (int cc = 0; cc * 32 < p.nblk; ++cc) {
               uint32_t r[32];
@@ -685,7 +689,9 @@ int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K,
   p.taps = R * S; p.S = S; p.ph = ph; p.W = Wo; p.shiftN = copies ? N : 0; p.rowmul = stride;
   p.n_blocks = (C + 255) / 256;
   p.nblk = round_up((C + p.n_blocks - 1) / p.n_blocks, 16);
-  const int MBtot = (K + 127) / 128;
+  int MBtot = (K + 127) / 128;
+  p.mrows = getenv("SPC_WG_ROWS128") ? 128 : round_up((K + MBtot - 1) / MBtot, 8);   // e.g. K = 416 -> 4 blocks of 104
+  MBtot = (K + p.mrows - 1) / p.mrows;
   int MG = p.taps > 1 ? 1 : 512 / p.nblk;
   if (MG > MBtot) MG = MBtot;
   MG = MG >= 4 ? 4 : (MG >= 2 ? 2 : 1);
@@ -693,7 +699,7 @@ int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K,
   p.chunks_per_image = (P + 63) / 64;
   p.chunks_total = p.chunks_per_image * N;
   CUtensorMap tdy, tx, tx4;
-  int rc = make_act_tmap(&tdy, dy, P, K, N, 128);
+  int rc = make_act_tmap(&tdy, dy, P, K, N, p.mrows);
   if (rc) return rc;
   if (p.taps > 1) {
     const uint64_t dims[4] = {(uint64_t)Wo, (uint64_t)Hin, (uint64_t)C, (uint64_t)N * (copies ? S : 1)};
