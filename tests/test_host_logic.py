@@ -87,3 +87,30 @@ def test_no_cpu_fallback():
 
 def test_north_star_aliases():
     assert spatial.pool_spatial is spatial.Pool and spatial.halo_exchange is spatial.halo_exchange_layer
+
+
+def test_dropin_import_shim_resolves_reference_imports():
+    """The import lines of the reference's benchmark scripts, unmodified, with mpi4dl_b200/dropin on
+    the path (fresh interpreter so sys.modules of this process stays clean)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path[:0] = [%r, %r]\n"
+        "from torchgems import parser\n"
+        "from torchgems.mp_pipeline import model_generator\n"
+        "from torchgems.train_spatial import train_model_spatial, split_input, get_shapes_spatial, verify_spatial_config\n"
+        "from torchgems.train_spatial_master import train_spatial_model_master, verify_spatial_master_config\n"
+        "from torchgems.gems_master import train_model_master\n"
+        "import torchgems.comm as gems_comm\n"
+        "from torchgems.spatial import conv_spatial, halo_exchange_layer, Pool\n"
+        "from models import resnet, resnet_spatial, amoebanet\n"
+        "from utils import get_depth, isPowerTwo\n"
+        "import mpi4dl_b200.torchgems.train_spatial as mine\n"
+        "assert train_model_spatial is mine.train_model_spatial and gems_comm.MPIComm.__module__.startswith('mpi4dl_b200')\n"
+        "assert get_depth(2, 12) == 110 and parser.get_parser().parse_args([]).split_size == 2\n"
+        "print('ok')\n") % (os.path.join(root, "mpi4dl_b200", "dropin"), root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
