@@ -40,12 +40,16 @@ def _builders(kind, args, mb, image_size, spatial_kw):
                                              **spatial_kw)
         return seq, seq_size, model
     from mpi4dl_b200.models import amoebanet
+    if args.halo_d2:                       # fused-halo cells: two wide exchanges per normal cell, valid convs after
+        from mpi4dl_b200.models import amoebanet_d2 as spatial_builder
+    else:
+        spatial_builder = amoebanet
     seq_size = min(512, image_size)
     seq = amoebanet.amoebanetd(num_classes=args.num_classes, num_layers=args.num_layers, num_filters=args.num_filters)
     kw = dict(spatial_kw)
     kw.pop("input_shape", None)
-    model = amoebanet.amoebanetd_spatial(num_classes=args.num_classes, num_layers=args.num_layers,
-                                         num_filters=args.num_filters, **kw)
+    model = spatial_builder.amoebanetd_spatial(num_classes=args.num_classes, num_layers=args.num_layers,
+                                               num_filters=args.num_filters, **kw)
     return seq, seq_size, model
 
 
@@ -87,8 +91,8 @@ def main(kind):
     num_spatial_parts = nsp[0] if len(nsp) == 1 else nsp
     P = nsp[0]
     balance = [int(v) for v in args.balance.split(",")] if args.balance else None
-    if args.halo_d2:
-        raise NotImplementedError("--halo-D2 model builders are not built yet (conv_spatial(halo_len=...) is)")
+    if args.halo_d2 and kind == "resnet":
+        raise NotImplementedError("--halo-D2 is built for AmoebaNet (models/amoebanet_d2.py); the ResNet D2 builder is not")
     if args.local_DP != 1:
         raise NotImplementedError("--local-DP > 1 is not built yet")
     verify_spatial_config(slice_method, image_size, nsp)

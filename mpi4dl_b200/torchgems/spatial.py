@@ -450,6 +450,59 @@ class Pool(nn.Module, _SpatialTopology):
         return _PoolFn.apply(x, desc_args, *strips)
 
 
+class local_conv2d(nn.Conv2d):
+    """Conv2d on ONE tile with no exchange, on the libspconv kernels.  The D2 ("fused halo") cells of
+    the reference feed plain nn.Conv2d(padding=0) -- cuDNN -- with tensors that already carry a wide
+    halo (amoebanet_d2.py:159-191, 297-311); this is their replacement.  The kernel computes the
+    "same"-padded convolution of the tile and the result is cropped to the padding actually asked
+    for: padding=0 gives the valid convolution (interior windows never see the zero padding, so
+    values are identical), padding=(k-1)//2 keeps everything.  Stride 1 only when cropping."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True):
+        super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding, bias=bias)
+        self._same = ((self.kernel_size[0] - 1) // 2, (self.kernel_size[1] - 1) // 2)
+        for p_, s_ in zip(self.padding, self._same):
+            assert p_ in (0, s_), "local_conv2d: padding must be 0 or (k-1)//2"
+        assert tuple(self.padding) == self._same or tuple(self.stride) == (1, 1), \
+            "local_conv2d: a valid (padding=0) convolution is supported for stride 1 only"
+        self.algo = _lib.SPC_ALGO_AUTO
+
+    def forward(self, tensor):
+        _require_cuda(tensor, "local_conv2d")
+        x = tensor.contiguous()
+        N, Cc, H, W = x.shape
+        ph, pw = self._same
+        desc_args = (N, Cc, H, W, self.out_channels, self.kernel_size[0], self.kernel_size[1], self.stride[0],
+                     self.stride[1], ph, pw, _lib.dtype_code(x.dtype), self.algo)
+        y = _ConvSpatialFn.apply(x, self.weight, self.bias, desc_args, *([None] * 9))
+        ch, cw = ph - self.padding[0], pw - self.padding[1]
+        if ch or cw:
+            y = y[:, :, ch:y.shape[2] - ch, cw:y.shape[3] - cw]
+        return y
+
+
+class local_pool2d(nn.Module):
+    """Max/Avg pooling of one tile with no exchange (D2 cells: nn.AvgPool2d(3, padding=0),
+    amoebanet_d2.py:88-117): the zero-padded pool of the tile, cropped when padding=0."""
+
+    def __init__(self, operation, kernel_size, stride=1, padding=0):
+        super().__init__()
+        assert operation in ("MaxPool2d", "AvgPool2d")
+        self.operation, self.kernel_size, self.stride, self.padding = operation, kernel_size, stride, padding
+        self._same = (kernel_size - 1) // 2
+        assert padding in (0, self._same) and (padding == self._same or stride == 1)
+
+    def forward(self, tensor):
+        _require_cuda(tensor, "local_pool2d")
+        x = tensor.contiguous()
+        N, Cc, H, W = x.shape
+        mode = _lib.SPC_POOL_MAX if self.operation == "MaxPool2d" else _lib.SPC_POOL_AVG
+        y = _PoolFn.apply(x, (N, Cc, H, W, self.kernel_size, self.stride, self._same, mode, _lib.dtype_code(x.dtype)),
+                          *([None] * 9))
+        c = self._same - self.padding
+        return y[:, :, c:y.shape[2] - c, c:y.shape[3] - c] if c else y
+
+
 # north_star aliases (BASELINE.json names that do not exist in the reference, SURVEY.md section 0)
 pool_spatial = Pool
 halo_exchange = halo_exchange_layer

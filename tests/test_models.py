@@ -34,8 +34,9 @@ def _sig(m):
 
 def _kinds(m):
     # (the reference's Pool wraps an inner nn pool named ".pool"; the generator skips those too)
-    ks = [(n, type(x).__name__) for n, x in m.named_modules()
-          if type(x).__name__ in ("Conv2d", "conv_spatial", "Pool")
+    alias = {"local_conv2d": "Conv2d", "local_pool2d": "AvgPool2d"}   # stand-ins for the D2 cells' plain convs / pools
+    ks = [(n, alias.get(type(x).__name__, type(x).__name__)) for n, x in m.named_modules()
+          if type(x).__name__ in ("Conv2d", "conv_spatial", "Pool", "halo_exchange_layer", "local_conv2d", "local_pool2d")
           or (type(x).__name__ in ("AvgPool2d", "MaxPool2d") and not n.endswith(".pool"))]
     return hashlib.sha256(repr(ks).encode()).hexdigest(), sum(t == "conv_spatial" for _, t in ks), sum(t == "Pool" for _, t in ks)
 
@@ -87,6 +88,16 @@ def test_amoebanet_spatial_structure(e):
     from mpi4dl_b200.models import amoebanet
     m = amoebanet.amoebanetd_spatial(local_rank=0, spatial_size=1, num_spatial_parts=4, slice_method="square", num_classes=10,
                                      num_layers=e["num_layers"], num_filters=e["num_filters"], **e["kw"])
+    _check(m, e)
+
+
+@pytest.mark.parametrize("e", GOLD["amoebanet_d2_spatial"],
+                         ids=lambda e: "L%d_mp%d_%s" % (e["num_layers"], e["kw"]["mp_size"], "bal" if e["kw"]["balance"] else "even"))
+def test_amoebanet_d2_spatial_structure(e):
+    """D2 (fused halo) builder: same keys, and halo_exchange_layer / conv / pool modules in the same places."""
+    from mpi4dl_b200.models import amoebanet_d2
+    m = amoebanet_d2.amoebanetd_spatial(local_rank=0, spatial_size=1, num_spatial_parts=4, slice_method="square", num_classes=10,
+                                        num_layers=e["num_layers"], num_filters=e["num_filters"], **e["kw"])
     _check(m, e)
 
 

@@ -27,7 +27,13 @@ def kinds(m):
     ks = []
     for n, x in m.named_modules():
         t = type(x).__name__
-        if t in ("Conv2d", "conv_spatial", "Pool") or (t in ("AvgPool2d", "MaxPool2d") and not n.endswith(".pool")):
+        if n.endswith(".halo_len_layer"):                  # inner layer of the reference's Pool
+            continue
+        if t in ("local_conv2d",):                         # this repo's stand-in for the D2 cells' plain convs / pools
+            t = "Conv2d"
+        if t in ("local_pool2d",):
+            t = "AvgPool2d"
+        if t in ("Conv2d", "conv_spatial", "Pool", "halo_exchange_layer") or (t in ("AvgPool2d", "MaxPool2d") and not n.endswith(".pool")):
             ks.append((n, t))
     return hashlib.sha256(repr(ks).encode()).hexdigest(), sum(t == "conv_spatial" for _, t in ks), sum(t == "Pool" for _, t in ks)
 
@@ -64,8 +70,8 @@ def main():
     ref_shim.install()
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29779")
     dist.init_process_group("gloo", rank=0, world_size=1)
-    from models import amoebanet, resnet, resnet_spatial
-    res = {"resnet": [], "resnet_spatial": [], "amoebanet": [], "amoebanet_spatial": []}
+    from models import amoebanet, amoebanet_d2, resnet, resnet_spatial
+    res = {"resnet": [], "resnet_spatial": [], "amoebanet": [], "amoebanet_spatial": [], "amoebanet_d2_spatial": []}
     for ver, depth in ((1, 20), (2, 29), (2, 101)):
         m = getattr(resnet, "get_resnet_v%d" % ver)((2, 3, 32, 32), depth)
         res["resnet"].append(dict(version=ver, depth=depth, **entry(m, 32)))
@@ -83,6 +89,9 @@ def main():
             ms = amoebanet.amoebanetd_spatial(local_rank=0, spatial_size=1, num_spatial_parts=4, slice_method="square",
                                               num_classes=10, num_layers=nl, num_filters=nf, **kw)
             res["amoebanet_spatial"].append(dict(num_layers=nl, num_filters=nf, kw=kw, **entry(ms)))
+            md = amoebanet_d2.amoebanetd_spatial(local_rank=0, spatial_size=1, num_spatial_parts=4, slice_method="square",
+                                                 num_classes=10, num_layers=nl, num_filters=nf, **kw)
+            res["amoebanet_d2_spatial"].append(dict(num_layers=nl, num_filters=nf, kw=kw, **entry(md)))
     json.dump({"source": "tools/gen_model_golden.py on unmodified /root/reference/src/models (CPU)", **res}, open(OUT, "w"), indent=1)
     print({k: len(v) for k, v in res.items()})
 
