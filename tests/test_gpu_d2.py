@@ -16,6 +16,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module", autouse=True)
 def _pg():
+    # the comparison side is cuDNN: keep it in true fp32 (TF32 convolutions are on by default and
+    # are ~1e-3 off, far coarser than libspconv's fp32 path)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     made = False
     if not dist.is_initialized():
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29785")

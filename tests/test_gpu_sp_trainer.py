@@ -35,6 +35,8 @@ def _batch(step):
 
 
 def _sequential_losses(width):
+    torch.backends.cudnn.allow_tf32 = False          # true-fp32 baseline (cuDNN defaults to TF32 convolutions)
+    torch.backends.cuda.matmul.allow_tf32 = False
     m = nn.Sequential(*_layers(lambda ci, co, k, s: nn.Conv2d(ci, co, k, stride=s, padding=k // 2),
                                lambda: nn.AvgPool2d(3, stride=1, padding=1), width)).cuda()
     opt = torch.optim.SGD(m.parameters(), lr=0.005, momentum=0.9)
