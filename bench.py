@@ -124,6 +124,54 @@ def pool_bytes(l, tile_h, tile_w, esz):
 
 
 # ------------------------------------------------------------------------------------------------
+def usable_cpus():
+    """Host threads this process can really use: scheduler affinity, capped by the cgroup CPU quota
+    (os.cpu_count() reports the machine, not the container)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+def cpu_reference_setup(layers, base_scale, budget_s):
+    """Thread count and sample size for the reference CPU path.  The reference gets its best
+    configuration: the thread count is calibrated (oversubscribing a container whose quota is below
+    the machine's core count makes the oneDNN path orders of magnitude slower, measured 68 s vs
+    0.3 s per pass), and the sample (all layers at 1/scale linear size) is the largest whose pass
+    fits `budget_s`.  Returns (threads, scale, seconds of one calibrated pass at base_scale)."""
+    import torch
+
+    from oracle import ref_port_torch as rp
+
+    n = usable_cpus()
+    cands = sorted({c for c in (n, n // 2, n // 4, 64, 32, 16, 8, 4) if 1 <= c <= n})
+    best_t, best_c = None, cands[0]
+    for c in cands:                                    # small to large; stop once it clearly gets worse
+        torch.set_num_threads(c)
+        rp.run_workload(layers, base_scale)            # per-shape warm-up at this thread count
+        t = rp.run_workload(layers, base_scale, warm=False)
+        if best_t is None or t < best_t:
+            best_t, best_c = t, c
+        elif t > 2.0 * best_t:
+            break
+    torch.set_num_threads(best_c)
+    scale, t = base_scale, best_t
+    # grow the sample while a pass is predicted to fit the budget; measured at every size because
+    # the cost grows faster than the area once the working set leaves the caches (x5 per halving)
+    while scale > 4 and 5.0 * t <= budget_s:
+        scale //= 2
+        rp.run_workload(layers, scale)
+        t = rp.run_workload(layers, scale, warm=False)
+    return best_c, scale, t
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU path (restated with the PyTorch CPU ops it calls,
     oracle/ref_port_torch.py) on a bounded sample of the workload, all host threads."""
@@ -135,19 +183,21 @@ def run_reference(args):
     if rank != 0:
         return
     d, desc = load_layers(args.workload)
-    scale = args.cpu_scale
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    rp.run_workload(d["layers"], scale)              # warm-up (primitive creation per shape)
-    times = [rp.run_workload(d["layers"], scale, warm=False) for _ in range(max(1, min(args.steps, 5)))]
+    steps = max(1, args.steps)
+    # whole run (warm-up + K timed passes) bounded to ~3 minutes
+    cores, scale, _ = cpu_reference_setup(d["layers"], args.cpu_scale, budget_s=min(20.0, 150.0 / (steps + max(1, args.warmup))))
+    for _ in range(max(0, args.warmup - 1)):         # (cpu_reference_setup already ran one warm pass at this size)
+        rp.run_workload(d["layers"], scale, warm=False)
+    times = [rp.run_workload(d["layers"], scale, warm=False) for _ in range(steps)]
     t = statistics.median(times)
     # the sample is the same layer list at 1/scale linear size: work per image scales with scale^2
     val = 1.0 / (t * scale * scale)
-    sample = "all %d layers fwd+bwd at %dx%d (1/%d linear size), fp32, torch CPU ops, extrapolated x%d to %d^2" % (
-        len(d["layers"]), d["image"] // scale, d["image"] // scale, scale, scale * scale, d["image"])
+    sample = ("all %d layers fwd+bwd at %dx%d (1/%d linear size), fp32, torch CPU ops, %d threads (calibrated; %d usable), "
+              "%.2f s per pass, extrapolated x%d to %d^2" % (len(d["layers"]), d["image"] // scale, d["image"] // scale, scale,
+                                                          cores, usable_cpus(), t, scale * scale, d["image"]))
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/sec", "n_gpus": args.gpus,
-        "steps": len(times), "warmup": 1, "ms_per_step": t * 1e3 * scale * scale, "higher_is_better": True,
+        "steps": len(times), "warmup": max(1, args.warmup), "ms_per_step": t * 1e3 * scale * scale, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "impl_note": "reference CPU path restated (pad + F.conv2d/F.*_pool2d + autograd)"},
         "cpu_baseline": {"value": val, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
@@ -418,15 +468,15 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             from oracle import ref_port_torch as rp
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
-            scale = args.cpu_scale * shrink
-            tcpu = rp.run_workload(d["layers"], scale)
+            cores, cscale, _ = cpu_reference_setup(d["layers"], args.cpu_scale * shrink, budget_s=12.0)
+            scale = cscale
+            tcpu = rp.run_workload(d["layers"], scale, warm=False)
             cpu = {"value": 1.0 / (tcpu * (scale / shrink) ** 2), "unit": "images/sec", "cores": cores, "kind": "port",
                    "sample": "all %d layers fwd+bwd at 1/%d linear size (%dx%d image) in fp32 with the torch CPU ops the "
                              "reference calls (oracle/ref_port_torch.py; per-shape warm-up excluded), %.1f s timed, "
-                             "extrapolated by area x%d" % (len(d["layers"]), scale, image // args.cpu_scale, image // args.cpu_scale,
-                                                          tcpu, (scale // shrink) ** 2)}
+                             "extrapolated by area x%d; %d threads (calibrated, %d usable)" % (
+                                 len(d["layers"]), scale // shrink, image * shrink // scale, image * shrink // scale, tcpu,
+                                 (scale // shrink) ** 2, cores, usable_cpus())}
         ms_step = ms_total / args.steps
         out = {
             "metric": METRIC, "value": 1000.0 / ms_step, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
