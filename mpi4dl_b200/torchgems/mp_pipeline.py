@@ -141,13 +141,20 @@ class train_model:
         self.initialize_send_recv_ranks()
 
     # ---- topology -----------------------------------------------------------------------------
+    def _replica_base(self, my_process_offset):
+        """First process rank of the pipeline replica this process belongs to.  The reference addresses
+        peers by their position on the rank line (:238-248), which is only right for the first replica;
+        with data-parallel replicas (world = k * mp_size) the peers of rank 5 are 4 and 6, not 0 and 2."""
+        return dist.get_rank() - my_process_offset if dist.is_initialized() else 0
+
     def initialize_send_recv_ranks(self):
         r = self.local_rank if not self.GEMS_INVERSE else self.mp_size - 1 - self.local_rank
         step = 1 if not self.GEMS_INVERSE else -1          # the inverse replica runs down the rank line
-        self.to_send_forward = r + step
-        self.to_recv_forward = r - step
-        self.to_send_backward = r - step
-        self.to_recv_backward = r + step
+        base = self._replica_base(r)
+        self.to_send_forward = base + r + step
+        self.to_recv_forward = base + r - step
+        self.to_send_backward = base + r - step
+        self.to_recv_backward = base + r + step
 
     def _parts_shape(self, shape):
         """shape_list already carries the micro-batch size: the scripts build model_generator with

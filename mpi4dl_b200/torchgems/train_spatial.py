@@ -135,8 +135,13 @@ class train_model_spatial(train_model):
 
     # ---- topology -----------------------------------------------------------------------------
     def _line(self, r):
-        """Position on the rank line -> process rank (the inverse replica is mirrored, :624-640)."""
-        return self.mp_size - 1 - r if self.GEMS_INVERSE else r
+        """Position on the rank line -> process rank (the inverse replica is mirrored, :624-640;
+        offset by the first rank of this model replica when the world holds several)."""
+        off = self.mp_size - 1 - r if self.GEMS_INVERSE else r
+        if not hasattr(self, "_base"):
+            mine = self.mp_size - 1 - self.local_rank if self.GEMS_INVERSE else self.local_rank
+            self._base = self._replica_base(mine)
+        return self._base + off
 
     def initialize_send_recv_ranks(self):
         P, r = self.num_spatial_parts, self.local_rank

@@ -1,0 +1,30 @@
+"""CPU smoke of the layer-parallel and GEMS-master benchmark scripts (torchrun, gloo): the same
+command lines as the reference's scripts, tiny shapes.  Includes a 4-process run with two
+data-parallel replicas of a 2-stage pipeline -- the configuration whose peer addressing the
+reference gets wrong (positions on the rank line used as process ranks)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+RUNS = [
+    ("lp_resnet_2", 2, "layer_parallelism/benchmark_resnet_lp.py",
+     "--split-size 2 --image-size 32 --batch-size 4 --parts 2 --steps 2"),
+    ("lp_amoebanet_2x2_replicas", 4, "layer_parallelism/benchmark_amoebanet_lp.py",
+     "--split-size 2 --image-size 64 --batch-size 2 --num-layers 3 --num-filters 64 --steps 2"),
+    ("gems_resnet_2", 2, "gems_master_model/benchmark_resnet_gems_master.py",
+     "--split-size 2 --image-size 32 --batch-size 2 --times 2 --steps 2"),
+]
+
+
+@pytest.mark.parametrize("idx,name,nproc,script,flags", [(i,) + r for i, r in enumerate(RUNS)], ids=[r[0] for r in RUNS])
+def test_benchmark_script_runs(idx, name, nproc, script, flags):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
+           "127.0.0.1", "--master-port", str(29750 + idx), os.path.join(ROOT, "benchmarks", script)] + flags.split()
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1"))
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "Mean " in out.stdout and "Global loss" in out.stdout, out.stdout[-2000:]
