@@ -344,6 +344,12 @@ int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& t
 }
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+// tuning knob: positive integer from the environment, else `dflt` (tools/wgrad_probe.py sweeps these)
+inline int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : 0;
+  return v > 0 ? v : dflt;
+}
 
 int make_act_tmap(CUtensorMap* m, const void* base, int P, int Cc, int N, int box_rows) {
   const uint64_t dims[3] = {(uint64_t)P, (uint64_t)Cc, (uint64_t)N};
@@ -645,6 +651,7 @@ int launch_wg(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMap& 
   const int stage_bytes = MG * A_BLK_BYTES + TG * b_slot;
   p.stages = (SMEM_LIMIT - SMEM_AUX) / stage_bytes;
   if (p.stages > 6) p.stages = 6;
+  p.stages = min(p.stages, env_int("SPC_WG_STAGES", p.stages));
   SPC_REQUIRE(p.stages >= 2, "tcgen05 wgrad: smem budget");
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -665,6 +672,7 @@ int launch_wg(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMap& 
     }
   }
   if (getenv("SPC_WG_SPLIT_CEIL")) splits = (2 * sms + groups - 1) / groups;   // previous behaviour (A/B knob)
+  splits = env_int("SPC_WG_SPLITS", splits);
   if (splits > p.chunks_total / 8) splits = p.chunks_total / 8;
   if (splits < 1) splits = 1;
   p.splits = splits;
@@ -687,13 +695,15 @@ int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K,
   WgParams p{};
   p.dw = dw; p.K = K; p.C = C; p.P = P; p.N = N;
   p.taps = R * S; p.S = S; p.ph = ph; p.W = Wo; p.shiftN = copies ? N : 0; p.rowmul = stride;
-  p.n_blocks = (C + 255) / 256;
+  const int nblk_max = min(256, round_up(env_int("SPC_WG_NBLK", 256), 16));   // accumulator width (input channels)
+  p.n_blocks = (C + nblk_max - 1) / nblk_max;
   p.nblk = round_up((C + p.n_blocks - 1) / p.n_blocks, 16);
   int MBtot = (K + 127) / 128;
   p.mrows = getenv("SPC_WG_ROWS128") ? 128 : round_up((K + MBtot - 1) / MBtot, 8);   // e.g. K = 416 -> 4 blocks of 104
   MBtot = (K + p.mrows - 1) / p.mrows;
   int MG = p.taps > 1 ? 1 : 512 / p.nblk;
   if (MG > MBtot) MG = MBtot;
+  MG = min(MG, env_int("SPC_WG_MG", MG));
   MG = MG >= 4 ? 4 : (MG >= 2 ? 2 : 1);
   p.mgroups = (MBtot + MG - 1) / MG;
   p.chunks_per_image = (P + 63) / 64;
