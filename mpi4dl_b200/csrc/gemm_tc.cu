@@ -687,6 +687,186 @@ int launch_wg(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMap& 
   return SPC_OK;
 }
 
+// ---- wgrad on CTA pairs (cta_group::2), 1x1 convolutions ------------------------------------------
+// EXPERIMENTAL, off unless SPC_WG_2CTA=1: written at the end of round 1 after the GPU budget was spent --
+// it compiles (ptxas/SASS checked) but has NOT run on hardware yet; tools/wgrad_probe.py --pair is
+// its first test.  Why: the single-CTA kernel loads MG*128 + nblk operand rows per 64-pixel chunk for
+// MG*128 x nblk accumulators (e.g. 256 + 240 rows); a pair computes M = 256*MP rows x nblk columns with each
+// CTA loading only ITS 128*MP rows of dY and HALF of the nblk rows of x (256 + 120 rows for the same
+// accumulators per CTA), 24-33 % fewer L2->SM bytes per MAC, and the smaller stage leaves room for 4 stages.
+template <int MP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+pw_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                     const WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int half = p.nblk / 2;                                // x rows (input channels) this CTA loads
+  const int b_bytes = half * 128;
+  const int b_slot = (b_bytes + 1023) & ~1023;
+  const int stage_bytes = MP * A_BLK_BYTES + b_slot;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* tfull = empty + MAX_STAGES;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                    // 0 = leader (issues the MMAs)
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    // full: leader's arrive.expect_tx + the peer's remote arrive; empty / tfull: one multicast commit;
+    // tempty (used in the leader only): the 128 epilogue threads of each CTA
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int ngroups = p.mgroups * p.n_blocks;                 // mgroups counts groups of MP row-PAIRS here
+  const int num_items = ngroups * p.splits;
+  const int per_split = (p.chunks_total + p.splits - 1) / p.splits;
+  const uint32_t stage_tx = 2u * (uint32_t)(MP * p.mrows * 128 + b_bytes);   // both CTAs' loads land on the leader's barrier
+
+#define WGP_DECODE(it)                                                          \
+  const int sp = (it) / ngroups;                                               \
+  const int g_ = (it) % ngroups;                                               \
+  const int nb = g_ % p.n_blocks;                                              \
+  const int mgp = g_ / p.n_blocks;                                             \
+  const int c_begin = sp * per_split, c_end = min(p.chunks_total, c_begin + per_split);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap_dy);
+      tma_prefetch_desc(&tmap_x);
+      int s = 0, ph = 0;
+      for (int it = cluster_id; it < num_items; it += num_clusters) {
+        WGP_DECODE(it)
+        for (int ch = c_begin; ch < c_end; ++ch) {
+          const int n = ch / p.chunks_per_image, p0 = (ch % p.chunks_per_image) * 64;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * stage_bytes;
+          if (rank == 0) mbar_arrive_expect_tx(&full[s], stage_tx);
+          else mbar_arrive_cluster(&full[s], 0);
+#pragma unroll
+          for (int i = 0; i < MP; ++i)      // row pair (mgp*MP + i): this CTA's 128-lane half
+            tma_load_3d_2sm(st + i * A_BLK_BYTES, &tmap_dy, &full[s], p0, ((mgp * MP + i) * 2 + (int)rank) * p.mrows, n);
+          tma_load_3d_2sm(st + MP * A_BLK_BYTES, &tmap_x, &full[s], p0, nb * p.nblk + (int)rank * half, n);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(256, p.nblk, 0, 0);
+      int s = 0, ph = 0, aph = 0;
+      for (int it = cluster_id; it < num_items; it += num_clusters) {
+        WGP_DECODE(it)
+        (void)nb; (void)mgp;
+        mbar_wait(tempty, aph ^ 1);
+        tc_fence_after();
+        for (int ch = c_begin; ch < c_end; ++ch) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          const uint32_t sb = sa + MP * A_BLK_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t bdesc = umma_desc(sb + ks * 32, 16, 1024);
+#pragma unroll
+            for (int i = 0; i < MP; ++i) {
+              const uint64_t adesc = umma_desc(sa + i * A_BLK_BYTES + ks * 32, 16, 1024);
+              umma_bf16_2sm(tmem_base + i * p.nblk, adesc, bdesc, idesc, (ch > c_begin || ks > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit_2sm(&empty[s]);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit_2sm(tfull);
+        aph ^= 1;
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int aph = 0;
+    for (int it = cluster_id; it < num_items; it += num_clusters) {
+      WGP_DECODE(it)
+      mbar_wait(tfull, aph);
+      tc_fence_after();
+      if (c_end > c_begin) {
+#pragma unroll 1
+        for (int i = 0; i < MP; ++i) {
+          const int rib = quarter * 32 + lane;
+          const int k = rib < p.mrows ? ((mgp * MP + i) * 2 + (int)rank) * p.mrows + rib : p.K;
+#pragma unroll 1
+          for (int cc = 0; cc * 32 < p.nblk; ++cc) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + i * p.nblk + cc * 32, r);
+            tmem_ld_wait();
+            if (k < p.K) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int cl = cc * 32 + j;
+                const int c = nb * p.nblk + cl;
+                if (cl < p.nblk && c < p.C) atomicAdd(&p.dw[(size_t)k * p.C + c], __uint_as_float(r[j]));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(tempty, 0);       // both CTAs release the accumulators on the leader's barrier
+      aph ^= 1;
+    }
+  }
+#undef WGP_DECODE
+  tc_fence_before();
+  cluster_sync_all();                       // no CTA may exit while its peer can still signal into it
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+}
+
+template <int MP>
+int launch_wg_pair(const CUtensorMap& tdy, const CUtensorMap& tx, WgParams p, cudaStream_t st) {
+  const int b_slot = ((p.nblk / 2) * 128 + 1023) & ~1023;
+  const int stage_bytes = MP * A_BLK_BYTES + b_slot;
+  p.stages = (SMEM_LIMIT - SMEM_AUX) / stage_bytes;
+  if (p.stages > 6) p.stages = 6;
+  p.stages = min(p.stages, env_int("SPC_WG_STAGES", p.stages));
+  SPC_REQUIRE(p.stages >= 2, "tcgen05 pair wgrad: smem budget");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int clusters = sms / 2;
+  const int groups = p.mgroups * p.n_blocks;
+  int splits = 1;
+  {
+    double best = 0.0;
+    const int smax = (2 * clusters) / groups > 1 ? (2 * clusters) / groups : 1;
+    for (int s = 1; s <= smax; ++s) {
+      const int items_s = groups * s, waves = (items_s + clusters - 1) / clusters;
+      const double eff = (double)items_s / ((double)waves * clusters);
+      if (eff > best + 1e-9) { best = eff; splits = s; }
+      else if (eff > best - 0.02 && waves == 2) { splits = s; if (eff > best) best = eff; }
+    }
+  }
+  splits = env_int("SPC_WG_SPLITS", splits);
+  if (splits > p.chunks_total / 8) splits = p.chunks_total / 8;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  const int smem = p.stages * stage_bytes + SMEM_AUX;
+  auto kern = pw_wgrad_pair_kernel<MP>;
+  SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  const int items = groups * p.splits;
+  const int grid = 2 * (items < clusters ? items : clusters);
+  kern<<<grid, TC_THREADS, smem, st>>>(tdy, tx, p);
+  count_launch();
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+
 // x: activations [N][C][Hin][Wo] (taps == 1: Hin == Ho) or their S column-shifted (and, for
 // stride 2, column-subsampled) copies [S][N][C][Hin][Wo].  Ho x Wo = extent of dy.
 int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K, int C, int N, int Ho, int Wo, int Hin,
@@ -722,6 +902,18 @@ int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K,
     rc = make_act_tmap(&tx, x, P, C, N, p.nblk);
     if (rc) return rc;
     tx4 = tx;
+  }
+  if (p.taps == 1 && getenv("SPC_WG_2CTA") && MBtot >= 2 && p.nblk % 16 == 0) {
+    // CTA pairs (experimental, see pw_wgrad_pair_kernel): row pairs of 2*mrows, MP pairs per item
+    const int npairs = (MBtot + 1) / 2;
+    int MP = 512 / p.nblk;
+    if (MP > npairs) MP = npairs;
+    MP = MP >= 2 ? 2 : 1;
+    p.mgroups = (npairs + MP - 1) / MP;
+    CUtensorMap txh;      // x boxes of nblk/2 channels: each CTA of a pair loads its half of the block
+    rc = make_act_tmap(&txh, x, P, C, N, p.nblk / 2);
+    if (rc) return rc;
+    return MP == 2 ? launch_wg_pair<2>(tdy, txh, p, st) : launch_wg_pair<1>(tdy, txh, p, st);
   }
   if (MG == 1) return launch_wg<1>(tdy, tx, tx4, p, st);
   if (MG == 2) return launch_wg<2>(tdy, tx, tx4, p, st);

@@ -1,6 +1,7 @@
 """Sweep the wgrad tiling knobs (SPC_WG_NBLK / _MG / _STAGES / _SPLITS, SPC_WG_GROUP_MAJOR,
 SPC_WG_ROWS128) over the heavy AmoebaNet-D wgrad shapes and print ms / TB/s / TFLOP/s per
 configuration.  One GPU, ~1 minute:   python tools/wgrad_probe.py [--quick]
+                                   timeout 90 python tools/wgrad_probe.py --pair --quick   (CTA-pair kernel)
 
 What it is for: the 1664->416 @1024^2 wgrad runs at 2.5 ms with DRAM 44 %, tensor pipe 44 % and
 L2->SM 5.8 TB/s (profiles/r1b_ncu_full_summary.csv) -- nothing saturated.  The sweep separates the
@@ -23,8 +24,17 @@ CONFIGS = [{}] + [dict(SPC_WG_NBLK=str(n), SPC_WG_MG=str(m)) for n, m in itertoo
     dict(SPC_WG_ROWS128="1")]
 
 
+PAIR_CONFIGS = [{}, dict(SPC_WG_2CTA="1"), dict(SPC_WG_2CTA="1", SPC_WG_STAGES="3"), dict(SPC_WG_2CTA="1", SPC_WG_NBLK="128")]
+
+
 def main():
     quick = "--quick" in sys.argv
+    global CONFIGS
+    if "--pair" in sys.argv:
+        # first run of the cta_group::2 kernel (never executed on hardware in round 1): ALWAYS under an outer
+        # `timeout 90`, results are compared with the single-CTA kernel's dw (MISMATCH flag)
+        CONFIGS = PAIR_CONFIGS
+        KNOBS.append("SPC_WG_2CTA")
     L = _lib.lib()
     dev = "cuda:0"
     sp = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
