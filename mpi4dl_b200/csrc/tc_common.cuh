@@ -143,13 +143,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
-// shared::cluster addresses carry the CTA rank; clearing bit 24 addresses the even (leader) CTA of a pair
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+// shared::cluster address of the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t cta) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(cta));
+  return ra;
+}
 // TMA load into THIS CTA's smem whose transaction bytes are credited to the LEADER CTA's mbarrier
+// (CUTLASS gets the leader's address by clearing bit 24 of its own, Sm100MmaPeerBitMask; mapa is the
+// architected way to say the same thing)
 __device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(map_to_cta(bar, 0)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {   // same warp id in both CTAs
