@@ -114,3 +114,31 @@ def test_dropin_import_shim_resolves_reference_imports():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
                          env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_halo_benchmark_known_answers_match_the_oracle():
+    """benchmarks/communication/halo/halo_common.py (numpy fixtures of the self-checking halo benchmarks)
+    against the oracle: exchanged padded tiles and the ones-weights convolution, every grid."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "benchmarks", "communication", "halo"))
+    import halo_common as hc
+    import numpy as np
+
+    from oracle import spatial_oracle as so
+    full = hc.full_image(2, 3, 16)
+    for method, P in (("square", 4), ("vertical", 4), ("horizontal", 2), ("vertical", 2)):
+        tiles = so.split(full, method, P)
+        for halo in (1, 3):
+            padded = so.halo_exchange_layer(tiles, method, halo)
+            for r in range(P):
+                assert np.array_equal(hc.tile(full, method, P, r), tiles[r])
+                got = padded[r]["y"] if isinstance(padded[r], dict) else padded[r]
+                assert np.array_equal(hc.expected_padded_tile(full, method, P, r, halo), got), (method, P, halo, r)
+        for kh, kw in ((3, 3), (1, 7), (7, 1)):
+            w = np.ones((4, 3, kh, kw), np.float32)
+            ref = so.conv_spatial(tiles, w, np.ones(4, np.float32), method, (1, 1), None)
+            for r in range(P):
+                assert np.array_equal(hc.expected_conv_tile(full, method, P, r, kh, kw, 4), ref[r]["y"].astype(np.float64)), \
+                    (method, P, kh, kw, r)
