@@ -54,9 +54,15 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
     set_error("cuTensorMapEncodeTiled entry point not available");
     return SPC_ECUDA;
   }
-  if (cudaFree(nullptr) != cudaSuccess) {   // bind the primary context to this (possibly autograd worker) thread
-    set_error("tcgen05 conv: no CUDA context on this thread");
-    return SPC_ECUDA;
+  // bind the primary context to this (possibly autograd worker) thread -- once per thread: cudaFree is not
+  // allowed while a stream is being captured into a CUDA graph, and it is not free either
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    if (cudaFree(nullptr) != cudaSuccess) {
+      set_error("tcgen05 conv: no CUDA context on this thread");
+      return SPC_ECUDA;
+    }
+    ctx_bound = true;
   }
   cuuint64_t gd[5], gs[5];
   cuuint32_t bx[5], es[5];
@@ -312,6 +318,35 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+// tuning knob: positive integer from the environment, else `dflt` (tools/wgrad_probe.py sweeps these)
+// Every knob is read from the environment ONCE per process (getenv on the launch path showed up in the
+// N=8 step, which is CPU-bound): a small table keyed by the name's address (names are string literals).
+struct EnvKnob { const char* name; const char* val; };
+EnvKnob g_env_tab[32];
+int g_env_n = 0;
+inline const char* env_get(const char* name) {
+  for (int i = 0; i < g_env_n; ++i)
+    if (g_env_tab[i].name == name) return g_env_tab[i].val;
+  const char* v = getenv(name);
+  if (g_env_n < 32) { g_env_tab[g_env_n].name = name; g_env_tab[g_env_n].val = v; ++g_env_n; }
+  return v;
+}
+inline int env_int(const char* name, int dflt) {
+  const char* e = env_get(name);
+  const int v = e ? atoi(e) : 0;
+  return v > 0 ? v : dflt;
+}
+inline int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
 constexpr int SMEM_LIMIT = 222 * 1024;   // leave room for a small co-resident kernel (halo post/collect, boundary strips)
 constexpr int SMEM_AUX = 1024 /*align*/ + 512 /*barriers*/;
 
@@ -331,24 +366,18 @@ int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& t
   SPC_REQUIRE(p.stages >= 2, "tcgen05 conv: shared memory budget too small (MB=%d kchunks=%d)", MB, kchunks);
   const int smem = (p.wres ? wres_bytes : 0) + p.stages * stage_bytes + p.out_bufs * OUT_BUF_BYTES + SMEM_AUX;
   auto kern = pw_gemm_kernel<MB>;
-  SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  const int sms = sm_count();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   if (p.num_tiles < 16 * sms) p.tgroup = 1;   // small problems: keep every SM busy
   kern<<<grid, TC_THREADS, smem, st>>>(tw, tx, tx4, ty, p);
   count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
-}
-
-inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-// tuning knob: positive integer from the environment, else `dflt` (tools/wgrad_probe.py sweeps these)
-inline int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  const int v = e ? atoi(e) : 0;
-  return v > 0 ? v : dflt;
 }
 
 int make_act_tmap(CUtensorMap* m, const void* base, int P, int Cc, int N, int box_rows) {
@@ -436,7 +465,7 @@ int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bi
   p.shiftN = copies ? c.N : 0;
   p.rowmul = cs;
   {
-    const char* e = getenv("SPC_TILE_GROUP");
+    const char* e = env_get("SPC_TILE_GROUP");
     p.tgroup = e ? atoi(e) : 1;   // measured: no effect on B200 (tools/stride_probe.py), kept as a knob
     if (p.tgroup < 1) p.tgroup = 1;
   }
@@ -447,8 +476,8 @@ int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bi
   // Measured (r1, profiles/): wins for Cin <= 416 (+6..19 %), loses for Cin >= 624 where the K loop is
   // long enough to hide the epilogue and the extra activation reads cost more than the overlap gains.
   int mb = MBtot >= 3 ? (c.Cin <= 512 ? 2 : 4) : MBtot;
-  if (MBtot >= 3 && getenv("SPC_PW_MB4")) mb = 4;                 // A/B knobs
-  if (MBtot >= 3 && getenv("SPC_PW_MB2")) mb = 2;
+  if (MBtot >= 3 && env_get("SPC_PW_MB4")) mb = 4;                 // A/B knobs
+  if (MBtot >= 3 && env_get("SPC_PW_MB2")) mb = 2;
   p.num_mg = (MBtot + mb - 1) / mb;
   p.tiles_per_image = (P + BN - 1) / BN;
   p.num_tiles = p.tiles_per_image * c.N * p.num_mg;
@@ -653,9 +682,7 @@ int launch_wg(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMap& 
   if (p.stages > 6) p.stages = 6;
   p.stages = min(p.stages, env_int("SPC_WG_STAGES", p.stages));
   SPC_REQUIRE(p.stages >= 2, "tcgen05 wgrad: smem budget");
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int groups = p.mgroups * p.n_blocks * p.passes;
   // items = groups * splits run on a persistent grid of `sms` CTAs: pick the split count whose item
   // count fills whole waves (2 waves when possible).  Rounding UP here left a third, nearly empty
@@ -671,15 +698,19 @@ int launch_wg(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMap& 
       else if (eff > best - 0.02 && waves == 2) { splits = s; if (eff > best) best = eff; }   // prefer two waves
     }
   }
-  if (getenv("SPC_WG_SPLIT_CEIL")) splits = (2 * sms + groups - 1) / groups;   // previous behaviour (A/B knob)
+  if (env_get("SPC_WG_SPLIT_CEIL")) splits = (2 * sms + groups - 1) / groups;   // previous behaviour (A/B knob)
   splits = env_int("SPC_WG_SPLITS", splits);
   if (splits > p.chunks_total / 8) splits = p.chunks_total / 8;
   if (splits < 1) splits = 1;
   p.splits = splits;
-  p.split_major = getenv("SPC_WG_GROUP_MAJOR") ? 0 : 1;            // A/B knob: previous item order
+  p.split_major = env_get("SPC_WG_GROUP_MAJOR") ? 0 : 1;            // A/B knob: previous item order
   const int smem = p.stages * stage_bytes + SMEM_AUX;
   auto kern = pw_wgrad_kernel<MG>;
-  SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
   const int items = groups * p.splits;
   kern<<<items < sms ? items : sms, TC_THREADS, smem, st>>>(tdy, tx, tx4, p);
   count_launch();
@@ -836,9 +867,7 @@ int launch_wg_pair(const CUtensorMap& tdy, const CUtensorMap& tx, WgParams p, cu
   if (p.stages > 6) p.stages = 6;
   p.stages = min(p.stages, env_int("SPC_WG_STAGES", p.stages));
   SPC_REQUIRE(p.stages >= 2, "tcgen05 pair wgrad: smem budget");
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int clusters = sms / 2;
   const int groups = p.mgroups * p.n_blocks;
   int splits = 1;
@@ -858,7 +887,11 @@ int launch_wg_pair(const CUtensorMap& tdy, const CUtensorMap& tx, WgParams p, cu
   p.splits = splits;
   const int smem = p.stages * stage_bytes + SMEM_AUX;
   auto kern = pw_wgrad_pair_kernel<MP>;
-  SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  static bool attr_set = false;
+  if (!attr_set) {
+    SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
   const int items = groups * p.splits;
   const int grid = 2 * (items < clusters ? items : clusters);
   kern<<<grid, TC_THREADS, smem, st>>>(tdy, tx, p);
@@ -879,7 +912,7 @@ int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K,
   p.n_blocks = (C + nblk_max - 1) / nblk_max;
   p.nblk = round_up((C + p.n_blocks - 1) / p.n_blocks, 16);
   int MBtot = (K + 127) / 128;
-  p.mrows = getenv("SPC_WG_ROWS128") ? 128 : round_up((K + MBtot - 1) / MBtot, 8);   // e.g. K = 416 -> 4 blocks of 104
+  p.mrows = env_get("SPC_WG_ROWS128") ? 128 : round_up((K + MBtot - 1) / MBtot, 8);   // e.g. K = 416 -> 4 blocks of 104
   MBtot = (K + p.mrows - 1) / p.mrows;
   int MG = p.taps > 1 ? 1 : 512 / p.nblk;
   if (MG > MBtot) MG = MBtot;
@@ -903,7 +936,7 @@ int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K,
     if (rc) return rc;
     tx4 = tx;
   }
-  if (p.taps == 1 && getenv("SPC_WG_2CTA") && MBtot >= 2 && p.nblk % 16 == 0) {
+  if (p.taps == 1 && env_get("SPC_WG_2CTA") && MBtot >= 2 && p.nblk % 16 == 0) {
     // CTA pairs (experimental, see pw_wgrad_pair_kernel): row pairs of 2*mrows, MP pairs per item
     const int npairs = (MBtot + 1) / 2;
     int MP = 512 / p.nblk;
@@ -1327,3 +1360,6 @@ int tc_conv_wgrad(const spc_conv_desc* d, const void* x, const void* dy, float* 
 }
 
 }  // namespace spc
+
+// tuning probes (tools/wgrad_probe.py) change SPC_* knobs inside one process: forget the cached values
+extern "C" void spc_reload_env(void) { spc::g_env_n = 0; }

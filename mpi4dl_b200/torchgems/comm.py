@@ -104,6 +104,10 @@ class MPIComm:
             self.LOCAL_DP_MP_Comm = None
         self.allreduce_grp = self.create_allreduce_comm()
         self.test_allreduce_comm(self.allreduce_grp)
+        if ENABLE_SPATIAL and torch.cuda.is_available():
+            # every rank is here: agree once on the halo transport (peer mailboxes vs torch.distributed P2P)
+            from . import halo_transport
+            halo_transport.negotiate(torch.device("cuda", torch.cuda.current_device()))
 
     # ---------------------------------------------------------------------------------------
     def get_split_rank(self, num_spatial_parts_list, local_rank):

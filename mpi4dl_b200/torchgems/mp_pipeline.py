@@ -17,6 +17,8 @@ sent in a fixed order), and receive buffers are plain `torch.empty`.
 """
 from collections import OrderedDict
 
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -274,5 +276,11 @@ class train_model:
         return loss, corrects
 
     def update(self):
+        """optimizer.step() + zero the gradients IN PLACE.  The reference calls zero_grad() (mp_pipeline.py:536-538),
+        which since torch 2.0 drops `p.grad` (set_to_none=True): that severs the views
+        train_spatial_model_master points into its flat gradient buffers (train_spatial_master.py:126-131), so
+        --enable-master-comm-opt would ship stale buffers from the second step on.  Zeroing in place keeps
+        the aliases and is numerically identical for every other trainer.  SPCONV_REFERENCE_ZERO_GRAD=1
+        restores the reference's call (used by the loss-sequence parity test)."""
         self.optimizer.step()
-        self.optimizer.zero_grad()
+        self.optimizer.zero_grad(set_to_none=os.environ.get("SPCONV_REFERENCE_ZERO_GRAD") == "1")

@@ -149,6 +149,7 @@ def _gems_worker(rank, case, port, q, zero_init):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["CUDA_VISIBLE_DEVICES"] = ""
     os.environ["SPCONV_GEMS_REFERENCE_ZERO_INIT"] = "1" if zero_init else "0"
+    os.environ["SPCONV_REFERENCE_ZERO_GRAD"] = "1" if zero_init else "0"   # the reference's zero_grad() (drops .grad)
     import gems_cases
     gems_cases.worker(rank, case, port, q, "ours")
 
@@ -185,6 +186,32 @@ def test_gems_sp_master_keeps_initial_parameters_by_default():
     import math
     first = got[3][0]
     assert abs(first - math.log(10)) > 1e-3 and math.isfinite(first)
+
+
+def test_update_keeps_flat_gradient_aliases():
+    """after train_model.update() the parameters' .grad must still be views of the flat gradient
+    buffer train_spatial_model_master ships between mirror ranks (zero_grad must not drop them)."""
+    import torch.nn as nn
+    from mpi4dl_b200.torchgems import mp_pipeline
+    from mpi4dl_b200.torchgems.train_spatial_master import train_spatial_model_master as M
+
+    os.environ.pop("SPCONV_REFERENCE_ZERO_GRAD", None)
+    model = nn.Sequential(nn.Linear(4, 3), nn.Linear(3, 2))
+    holder = M.__new__(M)
+    holder.device = torch.device("cpu")
+    size = sum(p.numel() for p in model.parameters())
+    flat_p, flat_g = M._flatten(holder, model, size)
+    tm = mp_pipeline.train_model.__new__(mp_pipeline.train_model)
+    tm.optimizer = torch.optim.SGD(model.parameters(), lr=0.1)
+    for step in range(2):
+        model(torch.randn(5, 4)).sum().backward()
+        assert flat_g.abs().sum() > 0                       # backward accumulated INTO the flat buffer
+        tm.update()
+        assert float(flat_g.abs().sum()) == 0.0             # zeroed in place
+        off = 0
+        for p_ in model.parameters():
+            assert p_.grad is not None and p_.grad.data_ptr() == flat_g[off:].data_ptr(), step
+            off += p_.numel()
 
 
 def test_spatial_master_config():

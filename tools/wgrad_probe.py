@@ -53,6 +53,7 @@ def main():
             for k in KNOBS:
                 os.environ.pop(k, None)
             os.environ.update(cfg)
+            L.spc_reload_env()
 
             def call():
                 _lib.check(L.spc_conv2d_wgrad(C.byref(d), x.data_ptr(), None, gy.data_ptr(), dw.data_ptr(), None, 0,
