@@ -207,6 +207,146 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def cudnn_baseline(torch, layers_unique, order, dev, steps, warmup):
+    """The competitor BASELINE.md section 4 names: the identical layer list on STOCK PyTorch ops on the
+    same B200 -- F.pad (the reference's ZeroPad2d copy, spatial.py:1020 / :1099, on every conv_spatial and
+    every k>=3 Pool) + F.conv2d / F.*_pool2d (cuDNN / ATen) + autograd backward -- NCHW like the reference,
+    cudnn.benchmark on so cuDNN picks its best algorithm.  Two arms: bf16 storage, and fp32 storage with
+    TF32 math (the reference's own dtype on tensor cores).  Same chain of independent layer fwd+bwd calls,
+    same scratch tensors, CUDA events."""
+    import torch.nn.functional as F
+
+    out = {}
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for arm, dt in (("bf16", torch.bfloat16), ("fp32_tf32", torch.float32)):
+            max_in = max(u["in_shape"][1] * u["in_shape"][2] * u["in_shape"][3] for u in layers_unique.values())
+            max_out = max(u["out_shape"][1] * u["out_shape"][2] * u["out_shape"][3] for u in layers_unique.values())
+            sx = torch.randn(max_in, dtype=dt, device=dev)
+            sg = torch.randn(max_out, dtype=dt, device=dev) * 0.01
+            ws = {}
+            for key, u in layers_unique.items():
+                l = u["layer"]
+                if l["op"] == "conv":
+                    ws[key] = (torch.randn(l["K"], l["C"], l["R"], l["S"], dtype=dt, device=dev) * 0.05).requires_grad_(True)
+
+            def run_layer(key):
+                u = layers_unique[key]
+                l = u["layer"]
+                n = u["in_shape"][1] * u["in_shape"][2] * u["in_shape"][3]
+                x = sx[:n].view(u["in_shape"]).detach()
+                if not u["first"]:
+                    x.requires_grad_(True)
+                m = u["out_shape"][1] * u["out_shape"][2] * u["out_shape"][3]
+                gy = sg[:m].view(u["out_shape"])
+                if l["op"] == "conv":
+                    xp = F.pad(x, (l["pad_w"], l["pad_w"], l["pad_h"], l["pad_h"])) if l.get("kind") == "conv_spatial" else x
+                    y = F.conv2d(xp, ws[key], None, (l["stride_h"], l["stride_w"]), 0)
+                else:
+                    xp = F.pad(x, (l["pad"],) * 4) if l["k"] >= 3 else x
+                    y = (F.max_pool2d if l["mode"] == "max" else F.avg_pool2d)(xp, l["k"], l["stride"], 0)
+                if y.requires_grad:
+                    y.backward(gy)
+                x.grad = None
+                if l["op"] == "conv":
+                    ws[key].grad = None
+
+            def ev(fn, reps):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / reps
+
+            def chain():
+                for key in order:
+                    run_layer(key)
+
+            for _ in range(max(2, warmup)):
+                chain()
+            step_ms = ev(chain, max(2, steps))
+            per = []
+            for key, u in layers_unique.items():
+                l = u["layer"]
+                if l["op"] == "conv":
+                    shape = "%d->%d %dx%d s%d @%dx%d" % (l["C"], l["K"], l["R"], l["S"], l["stride_h"], u["th"], u["tw"])
+                else:
+                    shape = "%s%d s%d C=%d @%dx%d" % (l["mode"], l["k"], l["stride"], l["C"], u["th"], u["tw"])
+                per.append(dict(shape=shape, count=u["count"], fwd_bwd_ms=round(ev(lambda k=key: run_layer(k), 3), 4)))
+            out[arm] = dict(ms_per_step=step_ms, images_per_sec=1000.0 / step_ms, per_layer=per)
+            del sx, sg, ws
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    out["what"] = ("stock F.pad + F.conv2d / F.*_pool2d + autograd (cuDNN/ATen, NCHW, cudnn.benchmark) over the same "
+                   "layer list and tile, CUDA events; fwd_bwd_ms = pad + fprop + dgrad + wgrad of one layer")
+    return out
+
+
+def model_stage_arm(torch, dev, dtype, image, steps, warmup):
+    """The REAL spatial stage: the first six cells (stem1-3 + cell1_normal1-3, with their BatchNorm / ReLU /
+    add / concat) of models.amoebanet.amoebanetd_spatial(18, 416) -- the module tree the reference's SP
+    scripts train -- forward + backward on one tile of `image`^2, next to the same six cells of the stock
+    (non-spatial) builder on cuDNN.  One GPU cannot hold the saved activations of the 8192^2 stage, so this arm
+    runs the N=4 tile (4096^2)."""
+    import torch.nn as nn
+
+    from mpi4dl_b200.models import amoebanet
+
+    def first6(m):
+        return nn.Sequential(*list(m.children())[:6])
+
+    res = {"image": image, "cells": "stem1, stem2, stem3, cell1_normal1..3", "dtype": str(dtype).replace("torch.", "")}
+    builders = (("libspconv", lambda: first6(amoebanet.amoebanetd_spatial(0, 1, 1, mp_size=2, slice_method="square", num_classes=10,
+                                                                         num_layers=18, num_filters=416))),
+                ("stock_cudnn", lambda: first6(amoebanet.amoebanetd(num_classes=10, num_layers=18, num_filters=416))))
+    old = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name, build in builders:
+            torch.manual_seed(0)
+            m = build().to(dev).to(dtype)
+            if name == "libspconv":
+                res["conv_modules"] = {}
+                for x in m.modules():
+                    if isinstance(x, nn.Conv2d):
+                        res["conv_modules"][type(x).__name__] = res["conv_modules"].get(type(x).__name__, 0) + 1
+            x = torch.randn(1, 3, image, image, device=dev, dtype=dtype)
+
+            def step():
+                y, _ = m(x)
+                y.backward(torch.ones_like(y))
+                for p_ in m.parameters():
+                    p_.grad = None
+
+            for _ in range(max(2, warmup)):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(max(2, steps)):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            res[name + "_ms"] = e0.elapsed_time(e1) / max(2, steps)
+            res[name + "_peak_GB"] = round(torch.cuda.max_memory_allocated(dev) / 1e9, 1)
+            del m, x
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats(dev)
+    except Exception as e:  # noqa: BLE001 -- an auxiliary arm must never take the bench line down
+        res["error"] = repr(e)[:300]
+    finally:
+        torch.backends.cudnn.benchmark = old
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -219,6 +359,10 @@ def main():
     ap.add_argument("--cpu-scale", type=int, default=32, help="linear down-scale of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--algo", default="auto", choices=["auto", "direct"])
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step from a CUDA graph (auto: when capture succeeds)")
+    ap.add_argument("--no-cudnn-baseline", action="store_true")
+    ap.add_argument("--no-model-stage", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -242,6 +386,9 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    if world > 1:
+        from mpi4dl_b200.torchgems import halo_transport
+        halo_transport.negotiate(dev)            # collective: peer mailboxes unless some rank cannot
     L = _lib.lib()
     import ctypes as C
     sm, cc = C.c_int(), C.c_int()
@@ -309,14 +456,13 @@ def main():
             n *= s
         return buf[:n].view(shape)
 
-    def step(e2e=False):
+    def step_body(from_host_image):
+        """One pass of the hot path: every layer fwd + bwd, gradient flatten, allreduce / P."""
         off = 0
         last = None
-        if e2e:
-            dev_img.copy_(host_img, non_blocking=True)
         for i, key in enumerate(order):
             u = uniq[key]
-            x = dev_img if (e2e and i == 0) else view(scratch_x, u["in_shape"])
+            x = dev_img if (from_host_image and i == 0) else view(scratch_x, u["in_shape"])
             x = x.detach()
             if not u["first"]:
                 x.requires_grad_(True)
@@ -332,9 +478,21 @@ def main():
         if world > 1:
             dist.all_reduce(flat_grads)                                   # comm.py:506-514
             flat_grads.div_(world)
+        return last.detach().float().sum().view(1)
+
+    graphs = {}
+
+    def step(e2e=False):
+        """e2e: the step's input image comes from pinned HOST memory and its result goes back to the host."""
         if e2e:
-            host_out.copy_(last.detach().float().sum().view(1), non_blocking=True)
-        return last
+            dev_img.copy_(host_img, non_blocking=True)
+        if graphs:
+            graphs["e2e" if e2e else "dev"][0].replay()
+            res = graphs["e2e" if e2e else "dev"][1]
+        else:
+            res = step_body(e2e)
+        if e2e:
+            host_out.copy_(res, non_blocking=True)
 
     def timed(nsteps, e2e):
         if world > 1:
@@ -356,15 +514,55 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step(False)
+    step(True)
+    torch.cuda.synchronize()
+    L.spc_launch_count(1)
+    step(False)                                    # launches of ONE step, counted on the eager path
+    torch.cuda.synchronize()
+    launches_per_step = int(L.spc_launch_count(0))
+
+    # ---- CUDA graph: the step is launch-bound on small tiles (N=8: ~1500 launches for ~24 ms of GPU work), so
+    # the whole step -- halo post/collect included, their sequence numbers live in device memory -- is captured
+    # once and replayed.  Same public-API calls, same kernels; only the CPU launch cost goes away.
+    graph_note = "off"
+    if args.graph != "off":
+        ok = 1
+        try:
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            g_dev = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_dev):
+                r_dev = step_body(False)
+            g_e2e = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_e2e, pool=g_dev.pool()):
+                r_e2e = step_body(True)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            ok = 0
+            graph_note = "capture failed, eager launches: " + repr(e)[:200]
+            if args.graph == "on":
+                raise
+        if world > 1:
+            flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if ok:
+            graphs["dev"] = (g_dev, r_dev)
+            graphs["e2e"] = (g_e2e, r_e2e)
+            graph_note = "whole step replayed from one CUDA graph (captured through the public torchgems.spatial API)"
+            for _ in range(2):
+                step(False)
+                step(True)
+        elif graph_note == "off":
+            graph_note = "capture failed on a peer rank, eager launches"
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t_wall0 = time.time()
-    L.spc_launch_count(1)
     ms_total = timed(args.steps, False)
-    launches = int(L.spc_launch_count(0))
+    launches = launches_per_step * args.steps
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    step(True)
     ms_e2e = timed(args.steps, True)
 
     # ---- per-kernel timing pass: every distinct layer-op through the C ABI, CUDA events ----------
@@ -453,6 +651,13 @@ def main():
                 roof["traffic_launch"] = {"launch": kk, "algorithmic_bytes": o["bytes"], "event_ms": round(o["ms"], 4),
                                           "achieved_GBps": round(o["bytes"] / o["ms"] / 1e6, 1), "ncu": tr[kk].get("source")}
                 break
+        # every launch shape an ncu --set full capture exists for, good and bad alike
+        roof["traffic_table"] = [
+            {"launch": o["shape"] + " " + o["op"], "kernel": o["kernel"], "algorithmic_bytes": o["bytes"],
+             "dram_bytes": tr[o["shape"] + " " + o["op"]]["dram_bytes"],
+             "ratio": round(tr[o["shape"] + " " + o["op"]]["dram_bytes"] / o["bytes"], 2),
+             "ncu": tr[o["shape"] + " " + o["op"]].get("source")}
+            for o in ops if (o["shape"] + " " + o["op"]) in tr]
     except Exception:
         pass
     # whole-step roofline (sum over layer-ops of max(F/P, B/BW))
@@ -478,22 +683,45 @@ def main():
                                  len(d["layers"]), scale // shrink, image * shrink // scale, image * shrink // scale, tcpu,
                                  (scale // shrink) ** 2, cores, usable_cpus())}
         ms_step = ms_total / args.steps
+        cudnn = None
+        if world == 1 and not args.no_cudnn_baseline:
+            try:
+                cudnn = cudnn_baseline(torch, uniq, order, dev, min(args.steps, 5), 2)
+                # where libspconv loses to stock cuDNN: our fprop+dgrad+wgrad (+ pool fwd+bwd) per layer vs its fwd_bwd
+                ours = {}
+                for o in ops:
+                    ours[o["shape"]] = ours.get(o["shape"], 0.0) + o["ms"]
+                for arm in ("bf16", "fp32_tf32"):
+                    for r in cudnn[arm]["per_layer"]:
+                        r["libspconv_ms"] = round(ours.get(r["shape"], float("nan")), 4)
+                cudnn["loses_to_cudnn_bf16"] = [r["shape"] for r in cudnn["bf16"]["per_layer"]
+                                                if r["libspconv_ms"] > r["fwd_bwd_ms"]]
+                cudnn["speedup_vs_cudnn_bf16_step"] = round(cudnn["bf16"]["ms_per_step"] / ms_step, 3)
+            except Exception as e:  # noqa: BLE001
+                cudnn = {"error": repr(e)[:300]}
+        stage = None
+        if world == 1 and not args.no_model_stage and args.workload == "amoebanet" and not args.image:
+            stage = model_stage_arm(torch, dev, dtype, 4096, 3, 2)
         out = {
-            "metric": METRIC, "value": 1000.0 / ms_step, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if args.workload == "amoebanet" else METRIC.replace("AmoebaNet-D 8192^2", "ResNet-v2-101 4096^2"),
+            "value": 1000.0 / ms_step, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": args.dtype if args.dtype != "fp32" else "f32", "data": "synthetic",
             "config": {"workload": desc if not args.image else desc + " [debug image %d]" % image,
                        "global_batch": 1, "parallelism": "sp%d-%s" % (world, method), "tile": [image // gr, image // gc],
                        "layers": len(order), "l2_policy": "inputs larger than L2 (every layer tensor >> 126 MB)",
                        "note": "conv_spatial + Pool layers AND the 1x1 nn.Conv2d layers inside the spatial cells, "
-                               "all through torchgems.spatial modules -> libspconv C ABI; BN/ReLU/concat excluded",
-                       "algo": args.algo, "sm_count": sm.value},
+                               "all through torchgems.spatial modules -> libspconv C ABI; BN/ReLU/concat excluded "
+                               "(model_stage times the real cells with them)",
+                       "algo": args.algo, "sm_count": sm.value, "launch_mode": graph_note},
             "e2e": {"value": 1000.0 / (ms_e2e / args.steps), "unit": "images/sec",
                     "h2d_bytes_per_step": host_img.numel() * host_img.element_size(), "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "cudnn_baseline": cudnn,
+            "model_stage": stage,
             "per_layer": per_layer,
         }
         os.write(real_stdout, (json.dumps(out) + "\n").encode())

@@ -10,10 +10,12 @@ small layer recipe, instead of one constructor function per op.  The module tree
 state-dict key: "stem2.reduce2.conv1.weight", "cell1_normal1.operations.3.module.4.weight", ...)
 is the reference's, so its checkpoints load.  Reference behaviours kept on purpose:
   * the op called max_pool_3x3 is a 3x3 *average* pool (amoebanet.py:108-125);
-  * FactorizedReduce uses two identical-offset 1x1 stride-2 convs (:56-76) and stays an ordinary
-    nn.Conv2d in spatial cells (a 1x1 stride-2 conv is tile-local for even tiles);
-  * conv_1x1 and the outer 1x1s of conv_3x3 are ordinary convs too (:241-276), the 1x7/7x1 op is
-    spatial throughout (:147-238);
+  * FactorizedReduce uses two identical-offset 1x1 stride-2 convs (:56-76); they need no exchange (a 1x1
+    stride-2 conv is tile-local for even tiles), so the reference leaves them plain nn.Conv2d (cuDNN) in
+    spatial cells.  Here they are `torchgems.spatial.local_conv2d` there: same parameters and state-dict
+    keys, but on the libspconv kernels -- no cuDNN convolution is left in a spatial stage;
+  * likewise conv_1x1 and the outer 1x1s of conv_3x3 (:241-276); the 1x7/7x1 op is conv_spatial
+    throughout (:147-238);
   * only pipeline stage 0 is spatial, and the cut-over cell is found with the reference's layer
     counter, which advances twice for stem2 and stem3 (:651-699).
 """
@@ -35,9 +37,15 @@ def _pair(v):
     return v if isinstance(v, tuple) else (v, v)
 
 
-def _conv(sp, cin, cout, k=1, stride=1, padding=0):
-    """bias-free conv; `sp` (dict of tile-binding kwargs) selects conv_spatial."""
+def _conv(sp, cin, cout, k=1, stride=1, padding=0, local=False):
+    """bias-free conv; `sp` (dict of tile-binding kwargs) selects conv_spatial.  `local`: a tile-local conv
+    INSIDE a spatial cell (the reference's plain nn.Conv2d there, amoebanet.py:241-276): same parameters and
+    state-dict keys, but run by libspconv (torchgems.spatial.local_conv2d) so that no cuDNN convolution is
+    left in a spatial stage."""
     if sp is None:
+        if local:
+            from ..torchgems.spatial import local_conv2d
+            return local_conv2d(cin, cout, k, stride=stride, padding=padding, bias=False)
         return nn.Conv2d(cin, cout, k, stride, padding, bias=False)
     from ..torchgems.spatial import conv_spatial
     return conv_spatial(in_channels=cin, out_channels=cout, kernel_size=k, stride=stride, padding=padding, bias=False, **sp)
@@ -65,12 +73,12 @@ def relu_conv_bn(sp, in_channels, out_channels, kernel_size=1, stride=1, padding
 
 
 class FactorizedReduce(nn.Module):
-    def __init__(self, in_channels, out_channels):
+    def __init__(self, in_channels, out_channels, local=False):
         super().__init__()
         self.relu = nn.ReLU(inplace=False)
         self.pad = nn.ZeroPad2d((0, 1, 0, 1))          # unused, kept for the module tree
-        self.conv1 = nn.Conv2d(in_channels, out_channels // 2, kernel_size=1, stride=2, bias=False)
-        self.conv2 = nn.Conv2d(in_channels, out_channels // 2, kernel_size=1, stride=2, bias=False)
+        self.conv1 = _conv(None, in_channels, out_channels // 2, 1, 2, local=local)
+        self.conv2 = _conv(None, in_channels, out_channels // 2, 1, 2, local=local)
         self.bn = nn.BatchNorm2d(out_channels)
 
     def forward(self, x):
@@ -80,16 +88,17 @@ class FactorizedReduce(nn.Module):
 
 def _make_op(name, sp, c, stride):
     q = c // 4
+    loc = sp is not None          # tile-local convs of a spatial cell run on libspconv too
     if name == "none":
-        return nn.Identity() if stride == 1 else FactorizedReduce(c, c)
+        return nn.Identity() if stride == 1 else FactorizedReduce(c, c, local=loc)
     if name in ("avg_pool_3x3", "max_pool_3x3"):
         return _pool(sp, "AvgPool2d", 3, stride, 1)
     if name == "max_pool_2x2":
         return _pool(sp, "MaxPool2d", 2, stride, 0)
     if name == "conv_1x1":
-        return _relu_conv_bn_chain([_conv(None, c, c, 1, stride)])
+        return _relu_conv_bn_chain([_conv(None, c, c, 1, stride, local=loc)])
     if name == "conv_3x3":
-        return _relu_conv_bn_chain([_conv(None, c, q), _conv(sp, q, q, 3, stride, 1), _conv(None, q, c)])
+        return _relu_conv_bn_chain([_conv(None, c, q, local=loc), _conv(sp, q, q, 3, stride, 1), _conv(None, q, c, local=loc)])
     if name == "conv_1x7_7x1":
         return _relu_conv_bn_chain([_conv(sp, c, q), _conv(sp, q, q, (1, 7), (1, stride), (0, 3)),
                                     _conv(sp, q, q, (7, 1), (stride, 1), (3, 0)), _conv(sp, q, c)])
@@ -128,7 +137,7 @@ class Cell(nn.Module):
         super().__init__()
         self.reduce1 = relu_conv_bn(sp, channels_prev, channels)
         if reduction_prev:
-            self.reduce2 = FactorizedReduce(channels_prev_prev, channels)
+            self.reduce2 = FactorizedReduce(channels_prev_prev, channels, local=sp is not None)
         elif channels_prev_prev != channels:
             self.reduce2 = relu_conv_bn(sp, channels_prev_prev, channels)
         else:

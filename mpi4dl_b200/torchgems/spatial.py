@@ -470,6 +470,8 @@ class local_conv2d(nn.Conv2d):
     def forward(self, tensor):
         _require_cuda(tensor, "local_conv2d")
         x = tensor.contiguous()
+        if x.dtype != self.weight.dtype:
+            raise RuntimeError("local_conv2d: input dtype %s != weight dtype %s" % (x.dtype, self.weight.dtype))
         N, Cc, H, W = x.shape
         ph, pw = self._same
         desc_args = (N, Cc, H, W, self.out_channels, self.kernel_size[0], self.kernel_size[1], self.stride[0],
