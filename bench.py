@@ -541,6 +541,7 @@ def main():
         except Exception as e:  # noqa: BLE001
             ok = 0
             graph_note = "capture failed, eager launches: " + repr(e)[:200]
+            sys.stderr.write("bench: CUDA graph capture failed: %r\n" % (e,))
             if args.graph == "on":
                 raise
         if world > 1:

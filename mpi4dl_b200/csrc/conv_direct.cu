@@ -265,8 +265,12 @@ int launch_conv_direct(const DirectConvParams& p, int dtype, cudaStream_t st) {
   dim3 grid((unsigned)((size_t)tiles_x * tiles_y * kblocks), p.in.N);
 #define SPC_LAUNCH_DC2(TT, VV, KK)                                                                                  \
   do {                                                                                                               \
-    SPC_CHECK_CUDA(cudaFuncSetAttribute(conv_direct_kernel<TT, VV, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                        200 * 1024));                                                                \
+    static bool attr_set = false;                                                                                    \
+    if (!attr_set) {                                                                                                 \
+      SPC_CHECK_CUDA(cudaFuncSetAttribute(conv_direct_kernel<TT, VV, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          200 * 1024));                                                              \
+      attr_set = true;                                                                                               \
+    }                                                                                                                \
     conv_direct_kernel<TT, VV, KK><<<grid, DC_THREADS, smem, st>>>(p, CB, tiles_x, kblocks);                         \
   } while (0)
 #define SPC_LAUNCH_DC(TT, VV)                                          \
@@ -394,13 +398,21 @@ int launch_wgrad_direct(const DirectWgradParams& p_in, int dtype, cudaStream_t s
   for (int tap0 = 0; tap0 < taps; tap0 += WG_TAPS) {
     const int nt = taps - tap0 < WG_TAPS ? taps - tap0 : WG_TAPS;
     if (dtype == SPC_BF16) {
-      SPC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_direct_kernel<__nv_bfloat16>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      static bool attr_bf16 = false;
+      if (!attr_bf16) {
+        SPC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_direct_kernel<__nv_bfloat16>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_bf16 = true;
+      }
       wgrad_direct_kernel<__nv_bfloat16><<<grid, WG_THREADS, smem, st>>>(p, kblocks, cblocks, tiles_x, tiles_y,
                                                                          tiles_per_cta, tap0, nt);
     } else {
-      SPC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_direct_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          200 * 1024));
+      static bool attr_f32 = false;
+      if (!attr_f32) {
+        SPC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_direct_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            200 * 1024));
+        attr_f32 = true;
+      }
       wgrad_direct_kernel<float><<<grid, WG_THREADS, smem, st>>>(p, kblocks, cblocks, tiles_x, tiles_y,
                                                                 tiles_per_cta, tap0, nt);
     }

@@ -22,6 +22,11 @@ namespace spc {
 
 using namespace tc;
 
+// conv_tap.cu: tap convolutions (stride 1, <= 128 output channels) without shifted copies
+bool tap_v2_supported(int M, int Cin, int R, int S, int H, int W, int N, int stride);
+int run_conv_tap_v2(const __nv_bfloat16* wp, int Mpad, int Cpad, const __nv_bfloat16* x, const __nv_bfloat16* bias,
+                    __nv_bfloat16* y, int M, int Cin, int R, int S, int ph, int H, int W, int N, cudaStream_t st);
+
 namespace {
 
 constexpr int TC_THREADS = 192;
@@ -47,8 +52,8 @@ EncodeTiledFn get_encode() {
 }
 
 // bf16 tensor map, rank <= 4; dims/strides innermost first (strides in BYTES for dims 1..).
-int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box) {
+int make_tmap_sw(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -73,7 +78,7 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
     if (i > 0) gs[i - 1] = strides_bytes[i];
   }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu] strides=[%llu,%llu]", (int)r, rank,
@@ -83,6 +88,11 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, 
     return SPC_ECUDA;
   }
   return SPC_OK;
+}
+
+int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box) {
+  return make_tmap_sw(m, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 // ---- weight repack: Wp[tap][m][c] (bf16, zero padded to [taps][Mpad][Cpad]) -----------------------
@@ -409,7 +419,8 @@ int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bi
   const int Ho = c.H / cs, Wo = c.W / cs;
   const int Pin = c.H * c.W, P = Ho * Wo;            // P: output pixels per image
   const int Mpad = round_up(c.M, 128), Cpad = round_up(c.Cin, BK);
-  const bool copies = (c.S > 1 || cs > 1) && taps > 1;   // column-shifted (and subsampled) copies of the input
+  const bool v2 = taps > 1 && !env_get("SPC_TAP_V1") && tap_v2_supported(c.M, c.Cin, c.R, c.S, c.H, c.W, c.N, cs);
+  const bool copies = (c.S > 1 || cs > 1) && taps > 1 && !v2;   // column-shifted (and subsampled) copies of the input
   const uintptr_t ws0 = reinterpret_cast<uintptr_t>(ws);
   const uintptr_t wp_addr = (ws0 + 1023) & ~(uintptr_t)1023;
   const size_t wp_bytes = c.prepacked ? 0 : (size_t)taps * Mpad * Cpad * 2;
@@ -428,6 +439,8 @@ int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bi
     SPC_CHECK_CUDA(cudaGetLastError());
     wp = wpm;
   }
+  if (v2)
+    return run_conv_tap_v2(wp, Mpad, Cpad, x, bias, y, c.M, c.Cin, c.R, c.S, c.ph, c.H, c.W, c.N, st);
   const __nv_bfloat16* xsrc = x;
   if (copies) {
     void* xs = reinterpret_cast<void*>(xs_addr);
@@ -1244,6 +1257,9 @@ size_t tc_workspace_bytes(const spc_conv_desc* d, int op) {
     b += align1k(2ull * d->N * d->K * Ho * Wo * 2) + align1k(4ull * d->N * d->C * Ho * Wo * 2) + 4096;
     return b;
   }
+  if (op != 2 && !env_get("SPC_TAP_V1") &&
+      tap_v2_supported(op == 1 ? d->C : d->K, op == 1 ? d->K : d->C, d->R, d->S, d->H, d->W, d->N, cs))
+    return b;               // conv_tap.cu forms the horizontal taps in shared memory: no copies
   if (d->S > 1 || cs > 1)   // S column-shifted (stride 2: also subsampled) copies of the conv input
     b += align1k((size_t)d->S * d->N * (op == 1 ? d->K : d->C) * d->H * Wo * 2) + 2048;
   return b;
@@ -1358,6 +1374,13 @@ int tc_conv_wgrad(const spc_conv_desc* d, const void* x, const void* dy, float* 
   }
   return run_wgrad(xb, dyb, dw, d->K, d->C, d->N, 1, d->H * d->W, 1, 1, 1, 0, 1, false, st);
 }
+
+int make_tmap_ex(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, int swizzle128) {
+  return make_tmap_sw(m, base, rank, dims, strides_bytes, box,
+                      swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+int tc_sm_count() { return sm_count(); }
 
 }  // namespace spc
 

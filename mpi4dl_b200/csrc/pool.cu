@@ -501,7 +501,12 @@ int launch_pool3_tma(const PoolParams& p, cudaStream_t st) {
   }
   // the driver-API encode needs a current context on THIS thread; a backward pass can be the first
   // CUDA work of an autograd worker thread, which the runtime binds only at its first runtime call
-  SPC_CHECK_CUDA(cudaFree(nullptr));
+  // (once per thread: cudaFree is not permitted while the stream is being captured into a CUDA graph)
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    SPC_CHECK_CUDA(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   const size_t planes = (size_t)p.in.N * p.in.C;
   CUtensorMap tm;
   const cuuint64_t gd[3] = {(cuuint64_t)p.in.W, (cuuint64_t)p.in.H, (cuuint64_t)planes};
@@ -520,10 +525,15 @@ int launch_pool3_tma(const PoolParams& p, cudaStream_t st) {
   const size_t nt = planes * tiles_w * tiles_h;
   SPC_REQUIRE(nt < (1u << 31), "pool: too many tiles");
   auto kern = pool3_s1_tma_kernel<T>;
-  SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static bool attr_set = false;   // per instantiation
+  static int sms = 0;
+  if (!attr_set) {
+    SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    attr_set = true;
+  }
   const int grid = nt < (size_t)(2 * sms) ? (int)nt : 2 * sms;
   kern<<<grid, P3_THREADS, G::SMEM_BYTES, st>>>(tm, p, tiles_w, tiles_h, (int)nt);
   count_launch();

@@ -153,6 +153,16 @@ CONV_CASES = [
     (52, 52, (3, 3), (2, 2), 32, 256, False),     # stride-2 3x3 on tcgen05 (column-subsampled copies)
     (104, 104, (3, 3), (2, 2), 8, 128, False),
     (3, 104, (3, 3), (2, 2), 16, 128, False),     # the AmoebaNet stem
+    # conv_tap.cu (stride-1 taps formed in shared memory): small / partial channel boxes, odd row counts
+    # (tile rows past the image), 5-wide filters, several 64-channel chunks, resident and streamed weights
+    (3, 16, (3, 3), (1, 1), 20, 64, True),
+    (16, 16, (3, 3), (1, 1), 7, 128, False),
+    (24, 40, (5, 5), (1, 1), 10, 64, True),
+    (128, 64, (3, 3), (1, 1), 6, 64, True),
+    (200, 104, (1, 7), (1, 1), 5, 128, False),
+    (104, 104, (1, 7), (1, 1), 3, 192, False),
+    (104, 104, (7, 1), (1, 1), 23, 64, False),
+    (52, 128, (7, 1), (1, 1), 2, 64, True),
 ]
 
 

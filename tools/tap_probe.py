@@ -1,0 +1,70 @@
+"""Dev probe (GPU): conv_tap.cu vs the round-1 shifted-copy path (SPC_TAP_V1=1) on the BASELINE tap shapes:
+correctness against each other and CUDA-event time of fprop / dgrad.
+    python tools/tap_probe.py [--quick]"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mpi4dl_b200 import _lib  # noqa: E402
+
+SHAPES = [  # C, K, R, S, H, W
+    (104, 104, 1, 7, 1024, 1024), (104, 104, 7, 1, 1024, 1024), (52, 52, 1, 7, 2048, 2048), (52, 52, 7, 1, 2048, 2048),
+    (16, 16, 3, 3, 4096, 4096), (64, 16, 3, 3, 4096, 4096), (64, 64, 3, 3, 2048, 2048), (128, 64, 3, 3, 2048, 2048),
+    (3, 16, 3, 3, 4096, 4096),
+]
+
+
+def main():
+    quick = "--quick" in sys.argv
+    L = _lib.lib()
+    dev = "cuda:0"
+    sp = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+    for (Cc, K, R, S, H, W) in (SHAPES[:2] if quick else SHAPES):
+        torch.manual_seed(0)
+        x = torch.randn(1, Cc, H, W, device=dev).to(torch.bfloat16)
+        gy = torch.randn(1, K, H, W, device=dev).to(torch.bfloat16)
+        w = (torch.randn(K, Cc, R, S, device=dev) / (Cc * R * S) ** 0.5).to(torch.bfloat16)
+        y = torch.empty(1, K, H, W, device=dev, dtype=torch.bfloat16)
+        dx = torch.empty_like(x)
+        d = _lib.ConvDesc(1, Cc, H, W, K, R, S, 1, 1, (R - 1) // 2, (S - 1) // 2, _lib.SPC_BF16, _lib.SPC_ALGO_TCGEN05)
+        res = {}
+        for mode in ("v2", "v1"):
+            if mode == "v1":
+                os.environ["SPC_TAP_V1"] = "1"
+            else:
+                os.environ.pop("SPC_TAP_V1", None)
+            L.spc_reload_env()
+            nb = max(L.spc_conv_workspace_bytes(C.byref(d), i) for i in range(2))
+            ws = torch.empty(nb + 16, dtype=torch.uint8, device=dev)
+            fns = {"fprop": lambda: _lib.check(L.spc_conv2d_fwd(C.byref(d), x.data_ptr(), None, w.data_ptr(), None, y.data_ptr(),
+                                                                ws.data_ptr(), nb, sp()), "fwd"),
+                   "dgrad": lambda: _lib.check(L.spc_conv2d_dgrad(C.byref(d), gy.data_ptr(), w.data_ptr(), dx.data_ptr(),
+                                                                  ws.data_ptr(), nb, sp()), "dgrad")}
+            for nm, fn in fns.items():
+                fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                res[(mode, nm)] = (e0.elapsed_time(e1) / 5, (y if nm == "fprop" else dx).float().clone())
+            del ws
+        gb = (Cc + K) * H * W * 2 / 1e9
+        tf = 2.0 * Cc * K * R * S * H * W / 1e12
+        for nm in ("fprop", "dgrad"):
+            a, b = res[("v2", nm)], res[("v1", nm)]
+            err = float((a[1] - b[1]).abs().max())
+            ref = float(b[1].abs().max())
+            print("%4d->%-4d %dx%d @%dx%d %-5s  v2 %7.3f ms (%5.2f TB/s %6.1f TF/s)   v1 %7.3f ms   x%.2f   maxdiff %.3g / %.3g %s" % (
+                Cc, K, R, S, H, W, nm, a[0], gb / a[0], tf / a[0] * 1e3, b[0], b[0] / a[0], err, ref,
+                "" if err <= 0.02 * ref else "MISMATCH"))
+    os.environ.pop("SPC_TAP_V1", None)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,14 +17,16 @@ import torch  # noqa: E402
 
 from mpi4dl_b200 import _lib  # noqa: E402
 
-SHAPES = [(1664, 416, 1024), (416, 416, 1024), (624, 416, 2048), (104, 208, 4096), (1248, 416, 1024)]
+SHAPES = [(1664, 416, 1024), (416, 416, 1024), (624, 416, 2048), (104, 208, 4096), (1248, 416, 1024), (104, 416, 1024),
+          (416, 104, 1024), (208, 208, 2048), (208, 52, 4096), (52, 208, 2048)]
 KNOBS = ["SPC_WG_NBLK", "SPC_WG_MG", "SPC_WG_STAGES", "SPC_WG_SPLITS", "SPC_WG_GROUP_MAJOR", "SPC_WG_ROWS128"]
 CONFIGS = [{}] + [dict(SPC_WG_NBLK=str(n), SPC_WG_MG=str(m)) for n, m in itertools.product((128, 192, 256), (1, 2, 4))] + [
     dict(SPC_WG_STAGES="2"), dict(SPC_WG_SPLITS="10"), dict(SPC_WG_SPLITS="42"), dict(SPC_WG_GROUP_MAJOR="1"),
     dict(SPC_WG_ROWS128="1")]
 
 
-PAIR_CONFIGS = [{}, dict(SPC_WG_2CTA="1"), dict(SPC_WG_2CTA="1", SPC_WG_STAGES="3"), dict(SPC_WG_2CTA="1", SPC_WG_NBLK="128")]
+PAIR_CONFIGS = [{}, dict(SPC_WG_2CTA="1"), dict(SPC_WG_2CTA="1", SPC_WG_STAGES="3"), dict(SPC_WG_2CTA="1", SPC_WG_NBLK="128"),
+                dict(SPC_WG_2CTA="1", SPC_WG_NBLK="192")]
 
 
 def main():
