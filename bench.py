@@ -33,6 +33,15 @@ WORKLOADS = {
 METRIC = "images/sec (device-timed, max over ranks) AmoebaNet-D 8192^2 hot path (spatial-stage conv/pool fwd+bwd)"
 
 
+_T0 = time.time()
+
+
+def _log(msg):
+    """progress on stderr (stdout carries the ONE JSON line)"""
+    sys.stderr.write("[bench %6.1fs] %s\n" % (time.time() - _T0, msg))
+    sys.stderr.flush()
+
+
 def load_layers(name):
     fn, desc = WORKLOADS[name]
     d = json.load(open(os.path.join(ROOT, "tests", "golden", fn)))
@@ -211,18 +220,20 @@ def cudnn_baseline(torch, layers_unique, order, dev, steps, warmup):
     """The competitor BASELINE.md section 4 names: the identical layer list on STOCK PyTorch ops on the
     same B200 -- F.pad (the reference's ZeroPad2d copy, spatial.py:1020 / :1099, on every conv_spatial and
     every k>=3 Pool) + F.conv2d / F.*_pool2d (cuDNN / ATen) + autograd backward -- NCHW like the reference,
-    cudnn.benchmark on so cuDNN picks its best algorithm.  Two arms: bf16 storage, and fp32 storage with
+    cuDNN's default algorithm heuristics as the reference runs it (cudnn.benchmark's exhaustive search takes
+    minutes at these sizes).  Two arms: bf16 storage, and fp32 storage with
     TF32 math (the reference's own dtype on tensor cores).  Same chain of independent layer fwd+bwd calls,
     same scratch tensors, CUDA events."""
     import torch.nn.functional as F
 
     out = {}
     old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = False
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
         for arm, dt in (("bf16", torch.bfloat16), ("fp32_tf32", torch.float32)):
+            _log("cudnn baseline arm %s" % arm)
             max_in = max(u["in_shape"][1] * u["in_shape"][2] * u["in_shape"][3] for u in layers_unique.values())
             max_out = max(u["out_shape"][1] * u["out_shape"][2] * u["out_shape"][3] for u in layers_unique.values())
             sx = torch.randn(max_in, dtype=dt, device=dev)
@@ -284,7 +295,7 @@ def cudnn_baseline(torch, layers_unique, order, dev, steps, warmup):
             torch.cuda.empty_cache()
     finally:
         torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
-    out["what"] = ("stock F.pad + F.conv2d / F.*_pool2d + autograd (cuDNN/ATen, NCHW, cudnn.benchmark) over the same "
+    out["what"] = ("stock F.pad + F.conv2d / F.*_pool2d + autograd (cuDNN/ATen, NCHW, default heuristics) over the same "
                    "layer list and tile, CUDA events; fwd_bwd_ms = pad + fprop + dgrad + wgrad of one layer")
     return out
 
@@ -307,9 +318,10 @@ def model_stage_arm(torch, dev, dtype, image, steps, warmup):
                                                                          num_layers=18, num_filters=416))),
                 ("stock_cudnn", lambda: first6(amoebanet.amoebanetd(num_classes=10, num_layers=18, num_filters=416))))
     old = torch.backends.cudnn.benchmark
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = False
     try:
         for name, build in builders:
+            _log("model stage arm %s" % name)
             torch.manual_seed(0)
             m = build().to(dev).to(dtype)
             if name == "libspconv":
@@ -512,10 +524,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    _log("warm-up")
     for _ in range(max(args.warmup, 3)):
         step(False)
     step(True)
     torch.cuda.synchronize()
+    _log("warm-up done")
     L.spc_launch_count(1)
     step(False)                                    # launches of ONE step, counted on the eager path
     torch.cuda.synchronize()
@@ -558,6 +572,7 @@ def main():
         elif graph_note == "off":
             graph_note = "capture failed on a peer rank, eager launches"
     torch.cuda.synchronize()
+    _log("launch mode: " + graph_note)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t_wall0 = time.time()
     ms_total = timed(args.steps, False)
@@ -565,6 +580,7 @@ def main():
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     ms_e2e = timed(args.steps, True)
+    _log("timed: %.2f ms/step, e2e %.2f ms/step" % (ms_total / args.steps, ms_e2e / args.steps))
 
     # ---- per-kernel timing pass: every distinct layer-op through the C ABI, CUDA events ----------
     def ev_time(fn, reps=3):
@@ -673,6 +689,7 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
+            _log("cpu baseline")
             from oracle import ref_port_torch as rp
             cores, cscale, _ = cpu_reference_setup(d["layers"], args.cpu_scale * shrink, budget_s=12.0)
             scale = cscale

@@ -46,6 +46,7 @@ struct TapParams {
   int raw_blk;               // bytes of one raw row block: cbox * (160 shift path | 128 direct path)
   int tiles_w, tiles_h, num_tiles;
   int a_resident, ast, ops;  // weights resident?; weight ring depth; operand ring depth
+  int rawb;                  // raw (activation row block) buffers in the ring: 2..MAXRING, sized by bytes in flight
   int rows_raw;              // NB + R - 1
   const __nv_bfloat16* bias;
   __nv_bfloat16* y;
@@ -113,11 +114,11 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
   const int a_blocks = p.a_resident ? taps * p.kchunks : p.ast;
   uint8_t* a_base = smem;
   uint8_t* raw_base = a_base + a_blocks * p.a_blk;
-  uint8_t* op_base = raw_base + 2 * p.rows_raw * RAW_BLK;
+  uint8_t* op_base = raw_base + p.rawb * p.rows_raw * RAW_BLK;
   uint8_t* bar_base = op_base + (SHIFT ? p.ops * NB * BLK : 0);
   uint64_t* raw_full = reinterpret_cast<uint64_t*>(bar_base);
-  uint64_t* raw_empty = raw_full + 2;
-  uint64_t* a_full = raw_empty + 2;
+  uint64_t* raw_empty = raw_full + MAXRING;
+  uint64_t* a_full = raw_empty + MAXRING;
   uint64_t* a_empty = a_full + MAXRING;
   uint64_t* op_full = a_empty + MAXRING;
   uint64_t* op_empty = op_full + MAXRING;
@@ -130,12 +131,12 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&raw_full[i], 1);
-      mbar_init(&raw_empty[i], SHIFT ? 128 : 1);   // shift path: released by the 128 shifter threads
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 128);
     }
     for (int i = 0; i < MAXRING; ++i) {
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&raw_empty[i], SHIFT ? 128 : 1);   // shift path: released by the 128 shifter threads
       mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
       mbar_init(&op_full[i], 128); mbar_init(&op_empty[i], 1);
     }
@@ -167,7 +168,7 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
           uint8_t* dst = raw_base + rb.s * p.rows_raw * RAW_BLK;
           for (int i = 0; i < p.rows_raw; ++i)
             tma_load_4d(dst + i * RAW_BLK, &tmap_x, &raw_full[rb.s], w0 - (SHIFT ? 8 : 0), h0 - p.ph + i, kc * 64, n_);
-          rb.next(2);
+          rb.next(p.rawb);
         }
       }
     }
@@ -231,7 +232,7 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             if (SHIFT) { umma_commit(&op_empty[ro.s]); ro.next(p.ops); }
             if (!p.a_resident) { umma_commit(&a_empty[ra.s]); ra.next(p.ast); }
           }
-          if (!SHIFT) { umma_commit(&raw_empty[rb.s]); rb.next(2); }
+          if (!SHIFT) { umma_commit(&raw_empty[rb.s]); rb.next(p.rawb); }
         }
         umma_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; aph ^= 1; }
@@ -250,7 +251,7 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
           for (int r = 0; r < p.R; ++r)
             ShiftRow<NB, S, 0>::run(rawb + r * RAW_BLK, RAW_BLK, cv, tid, op_base, op_full, op_empty, ro, p.ops);
           mbar_arrive(&raw_empty[rb.s]);      // all 128 shifter threads are done reading this raw buffer
-          rb.next(2);
+          rb.next(p.rawb);
         }
       }
     }
@@ -326,29 +327,27 @@ bool plan_tap(int M, int Cin, int R, int S, int H, int W, int N, TapPlan* out) {
   for (int NB = 4; NB >= 2; NB -= 2) {
     if (NB == 4 && H < 4) continue;
     p.rows_raw = NB + R - 1;
-    const int raw_bytes = 2 * p.rows_raw * raw_blk;
+    const int raw_buf = p.rows_raw * raw_blk;                   // one raw buffer (all row blocks of a chunk)
+    const int op_tile = NB * BLK;
     const int a_res = taps * p.kchunks * p.a_blk;
     for (int resident = 1; resident >= 0; --resident) {
-      int a_bytes, ast = 0;
-      if (resident) {
-        a_bytes = a_res;
-      } else {
-        ast = 4;
-        a_bytes = ast * p.a_blk;
-      }
-      int rem = budget - a_bytes - raw_bytes;
-      int ops = 0;
-      if (shift) {
-        ops = rem / (NB * BLK);
-        if (ops > 6) ops = 6;
-        if (ops < 2) continue;
-        rem -= ops * NB * BLK;
-      }
+      // minimum configuration: 2 raw buffers, (shift) 2 operand tiles, weights resident or a ring of 4 blocks
+      int ast = resident ? 0 : 4;
+      int a_bytes = resident ? a_res : ast * p.a_blk;
+      int rawb = 2, ops = shift ? 2 : 0;
+      int rem = budget - a_bytes - rawb * raw_buf - ops * op_tile;
       if (rem < 0) continue;
-      if (!resident && !shift && rem >= 2 * p.a_blk) ast = min(MAXRING, ast + rem / p.a_blk), a_bytes = ast * p.a_blk;
-      p.a_resident = resident; p.ast = ast; p.ops = ops;
+      // spend what is left on bytes in flight: the loads are latency-bound (~1.5 us from L2 under load), so
+      // the TMA rings should hold ~100 KB beyond what the MMA is reading.  Order: operand ring to 3 (shifter /
+      // MMA decoupling), weight ring to 8, then raw buffers.
+      if (shift && rem >= op_tile) { ++ops; rem -= op_tile; }
+      while (!resident && ast < MAXRING && rem >= p.a_blk) { ++ast; rem -= p.a_blk; }
+      while (rawb < MAXRING && rem >= raw_buf) { ++rawb; rem -= raw_buf; }
+      while (shift && ops < 4 && rem >= op_tile) { ++ops; rem -= op_tile; }
+      a_bytes = resident ? a_res : ast * p.a_blk;
+      p.a_resident = resident; p.ast = ast; p.ops = ops; p.rawb = rawb;
       out->NB = NB; out->p = p;
-      out->smem = a_bytes + raw_bytes + (shift ? ops * NB * BLK : 0) + TAP_SMEM_AUX;
+      out->smem = a_bytes + rawb * raw_buf + ops * op_tile + TAP_SMEM_AUX;
       return true;
     }
   }

@@ -732,9 +732,8 @@ int launch_wg(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMap& 
 }
 
 // ---- wgrad on CTA pairs (cta_group::2), 1x1 convolutions ------------------------------------------
-// EXPERIMENTAL, off unless SPC_WG_2CTA=1: written at the end of round 1 after the GPU budget was spent --
-// it compiles (ptxas/SASS checked) but has NOT run on hardware yet; tools/wgrad_probe.py --pair is
-// its first test.  Why: the single-CTA kernel loads MG*128 + nblk operand rows per 64-pixel chunk for
+// Default for 1x1 convolutions with >= 400 input channels (see run_wgrad; verified against the single-CTA
+// kernel and against cuDNN fp32 by tests/test_gpu_fullsize_parity.py).  Why: the single-CTA kernel loads MG*128 + nblk operand rows per 64-pixel chunk for
 // MG*128 x nblk accumulators (e.g. 256 + 240 rows); a pair computes M = 256*MP rows x nblk columns with each
 // CTA loading only ITS 128*MP rows of dY and HALF of the nblk rows of x (256 + 120 rows for the same
 // accumulators per CTA), 24-33 % fewer L2->SM bytes per MAC, and the smaller stage leaves room for 4 stages.
@@ -949,7 +948,11 @@ int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K,
     if (rc) return rc;
     tx4 = tx;
   }
-  if (p.taps == 1 && env_get("SPC_WG_2CTA") && MBtot >= 2 && p.nblk % 16 == 0) {
+  // CTA pairs (cta_group::2): measured on B200 (tools/wgrad_probe.py --pair, profiles/r2_wgrad_pair.txt): x1.11..1.32
+  // for >= 416 input channels (624->416 @2048^2: 4.95 -> 3.74 ms), break-even at 416->104 / 208->52, slower for
+  // the HBM-bound narrow layers (104->208: x0.75, 52->208: x0.67).  SPC_WG_2CTA=1 / SPC_WG_1CTA=1 force either.
+  const bool pair = env_get("SPC_WG_2CTA") ? true : (env_get("SPC_WG_1CTA") ? false : C >= 400);
+  if (p.taps == 1 && pair && MBtot >= 2 && p.nblk % 16 == 0) {
     // CTA pairs (experimental, see pw_wgrad_pair_kernel): row pairs of 2*mrows, MP pairs per item
     const int npairs = (MBtot + 1) / 2;
     int MP = 512 / p.nblk;

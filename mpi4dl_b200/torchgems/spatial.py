@@ -122,12 +122,22 @@ class _SpatialTopology:
                 self.rank_neighbours.append(self.local_rank + dr * cols + dc)
             else:
                 self.rank_neighbours.append(-1)
-        # GEMS inverse replica lives on mirrored ranks (spatial.py:912-919)
+        # Which world ranks hold the neighbour tiles.  The reference knows two cases (spatial.py:912-919): the
+        # layer's local_rank IS this process's world rank, or -- GEMS inverse replica -- the replica lives on
+        # the mirrored rank line (world_size-1-r).  A third case exists once pipelines are data-parallel
+        # (world = k * mp_size, mp_pipeline's replica base): the tile line starts at this replica's first rank.
         if dist.is_available() and dist.is_initialized() and self.local_rank != dist.get_rank():
-            world_size = dist.get_world_size()
-            for i in range(9):
-                if self.neighbours[i] == 1:
-                    self.rank_neighbours[i] = world_size - 1 - self.rank_neighbours[i]
+            world_size, rank = dist.get_world_size(), dist.get_rank()
+            if world_size - 1 - rank == self.local_rank:
+                for i in range(9):
+                    if self.neighbours[i] == 1:
+                        self.rank_neighbours[i] = world_size - 1 - self.rank_neighbours[i]
+            else:
+                base = rank - self.local_rank
+                assert base > 0, "conv_spatial: local_rank %d does not belong to world rank %d" % (self.local_rank, rank)
+                for i in range(9):
+                    if self.neighbours[i] == 1:
+                        self.rank_neighbours[i] += base
 
     def set_tags(self):
         # kept for API compatibility (spatial.py:170-172); stream/flag ordering replaces MPI tags

@@ -162,7 +162,7 @@ CONV_CASES = [
     (200, 104, (1, 7), (1, 1), 5, 128, False),
     (104, 104, (1, 7), (1, 1), 3, 192, False),
     (104, 104, (7, 1), (1, 1), 23, 64, False),
-    (52, 128, (7, 1), (1, 1), 2, 64, True),
+    (52, 128, (7, 1), (1, 1), 4, 64, True),
 ]
 
 

@@ -19,10 +19,11 @@ SHAPES = [  # C, K, R, S, H, W
 
 def main():
     quick = "--quick" in sys.argv
+    only = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--only=")]      # shape index, v2 only (for ncu)
     L = _lib.lib()
     dev = "cuda:0"
     sp = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
-    for (Cc, K, R, S, H, W) in (SHAPES[:2] if quick else SHAPES):
+    for (Cc, K, R, S, H, W) in ([SHAPES[i] for i in only] if only else (SHAPES[:2] if quick else SHAPES)):
         torch.manual_seed(0)
         x = torch.randn(1, Cc, H, W, device=dev).to(torch.bfloat16)
         gy = torch.randn(1, K, H, W, device=dev).to(torch.bfloat16)
@@ -31,7 +32,7 @@ def main():
         dx = torch.empty_like(x)
         d = _lib.ConvDesc(1, Cc, H, W, K, R, S, 1, 1, (R - 1) // 2, (S - 1) // 2, _lib.SPC_BF16, _lib.SPC_ALGO_TCGEN05)
         res = {}
-        for mode in ("v2", "v1"):
+        for mode in (("v2",) if only else ("v2", "v1")):
             if mode == "v1":
                 os.environ["SPC_TAP_V1"] = "1"
             else:
@@ -57,6 +58,9 @@ def main():
         gb = (Cc + K) * H * W * 2 / 1e9
         tf = 2.0 * Cc * K * R * S * H * W / 1e12
         for nm in ("fprop", "dgrad"):
+            if only:
+                print("%4d->%-4d %dx%d @%dx%d %-5s  v2 %7.3f ms" % (Cc, K, R, S, H, W, nm, res[("v2", nm)][0]))
+                continue
             a, b = res[("v2", nm)], res[("v1", nm)]
             err = float((a[1] - b[1]).abs().max())
             ref = float(b[1].abs().max())
