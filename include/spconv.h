@@ -117,6 +117,26 @@ int spc_pool2d_fwd(const spc_pool_desc* d, const void* x, const spc_halo* halo, 
 int spc_pool2d_bwd(const spc_pool_desc* d, const void* x, const spc_halo* halo, const void* dy,
                    void* dx, void* stream);
 
+/* ---- fused BatchNorm2d (training mode, per-tile statistics) + ReLU ------------------------ *
+ * The cells of the spatial stages chain ReLU -> conv -> nn.BatchNorm2d (models/amoebanet.py:365-398 of the
+ * reference) / BatchNorm2d -> ReLU -> conv (resnet_spatial.py:165-180) as separate eager kernels; statistics
+ * are over the LOCAL tile only.  These four entry points do normalisation + the following ReLU
+ * in one HBM pass each way.  y, z, dz, dy: [N][C][H*W] (NCHW, H*W % 8 == 0), dtype SPC_F32 | SPC_BF16;
+ * all per-channel vectors are fp32 device arrays of C elements.
+ *   spc_bn_stats     : sum[c] = sum y, sumsq[c] = sum y^2                          (replaces the statistics pass)
+ *   spc_bn_apply     : z = relu?((y - mean[c]) * rstd[c] * gamma[c] + beta[c])     (BN apply + nn.ReLU)
+ *   spc_bn_bwd_reduce: dsum[c] = sum g, dsumx[c] = sum g * xhat, g = dz * [z > 0]  (= dbeta, dgamma)
+ *   spc_bn_bwd_apply : dy = gamma * rstd * (g - dsum/M - xhat * dsumx/M), M = N*H*W */
+int spc_bn_stats(int N, int C, long long HW, int dtype, const void* y, float* sum, float* sumsq, void* stream);
+int spc_bn_apply(int N, int C, long long HW, int dtype, const void* y, const float* mean, const float* rstd,
+                 const float* gamma, const float* beta, int relu, void* z, void* stream);
+int spc_bn_bwd_reduce(int N, int C, long long HW, int dtype, const void* dz, const void* y, const float* mean,
+                      const float* rstd, const float* gamma, const float* beta, int relu, float* dsum,
+                      float* dsumx, void* stream);
+int spc_bn_bwd_apply(int N, int C, long long HW, int dtype, const void* dz, const void* y, const float* mean,
+                     const float* rstd, const float* gamma, const float* beta, int relu, const float* dsum,
+                     const float* dsumx, void* dy, void* stream);
+
 /* ---- halo strips ------------------------------------------------------------------------ */
 /* Pack the strips a tile SENDS (spatial.py:336-357: the first/last halo rows/cols inside the
  * tile, .clone()d per direction) into send[d] for every d with send[d] != NULL.  send[d] may be

@@ -15,8 +15,8 @@
 //   * accumulators (NB*64 pixels x 128 channels, double buffered) live in TMEM; epilogue threads own one
 //     output channel each and store contiguous NCHW runs straight from registers.
 //
-// Warp roles (352 threads): 0 = activation TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue,
-// 6..9 = shifter, 10 = weight TMA producer.  All hand-offs are mbarriers; persistent CTAs, one per SM.
+// Warp roles (448 threads): 0 = TMA producer (activation row blocks and weight blocks, interleaved), 1 = MMA issuer
+// (+TMEM alloc), 2..5 = epilogue, 6..13 = shifter.  All hand-offs are mbarriers; persistent CTAs, one per SM.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -30,7 +30,7 @@ int tc_sm_count();
 
 namespace {
 
-constexpr int TAP_THREADS = 352;
+constexpr int TAP_THREADS = 448;
 constexpr int BLK = 8192;          // one operand block: [64 ch][64 px] bf16, 128-byte rows, SWIZZLE_128B
 constexpr int RAW_SHIFT_ROW = 160;  // raw row block of the shift path: [cbox ch][80 px], dense rows of 160 B
 constexpr int MAXRING = 8;
@@ -57,12 +57,11 @@ struct RingState {
   __device__ __forceinline__ void next(int n) { if (++s == n) { s = 0; ph ^= 1; } }
 };
 
-// 8 output pixels = the 24-pixel window [a | b | c] (three aligned 16-byte chunks) shifted by D pixels
+// 8 output pixels = the 16-pixel window w[0..7] (pixels -4 .. +11 around the chunk) shifted by D pixels, |D| <= 4
 template <int D>
-__device__ __forceinline__ uint4 shift_window(const uint4& a, const uint4& b, const uint4& c) {
-  static_assert(D >= -8 && D <= 8, "shift range");
-  const uint32_t w[13] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, 0u};
-  constexpr int e0 = 8 + D;
+__device__ __forceinline__ uint4 shift_window(const uint32_t (&w)[8]) {
+  static_assert(D >= -4 && D <= 4, "shift range");
+  constexpr int e0 = 4 + D;
   constexpr int k = e0 >> 1;
   uint4 o;
   if (e0 & 1) {
@@ -76,29 +75,54 @@ __device__ __forceinline__ uint4 shift_window(const uint4& a, const uint4& b, co
   return o;
 }
 
-// One filter row of the shifter's work: for every filter column SI (compile-time shift SI - S/2) wait for a free
-// operand-ring slot, write the tile's NB blocks [cv channels][64 pixels] in the swizzled MN-major layout, publish.
+constexpr int SHIFT_THREADS = 256;   // 8 shifter warps; thread -> (16-byte chunk q = tid & 7, channel c0 = tid >> 3 (+32))
+
+// The shifter's work for ONE filter row r of one (tile, chunk): every thread first loads the pixel windows of its
+// <= 2*NB items (block j, channel c, chunk q) into registers -- one aligned 16-byte load each, the 4 pixels on
+// either side come from the neighbour lanes by shuffle (the first / last chunk of a row read the 8-pixel slack
+// of the raw block instead) -- and then, for every filter column SI (compile-time shift SI - S/2), waits for a free
+// operand-ring slot, writes its items in the swizzled MN-major layout and publishes the tile.  Shared-memory reads:
+// once per filter ROW instead of three times per TAP.
 template <int NB, int S, int SI>
 struct ShiftRow {
-  static __device__ __forceinline__ void run(const uint8_t* rawr, int raw_blk, int cv, int tid, uint8_t* op_base,
-                                             uint64_t* op_full, uint64_t* op_empty, RingState& ro, int ops) {
+  static __device__ __forceinline__ void stores(const uint32_t (&win)[2 * NB][8], int cv, int tid, uint8_t* op_base,
+                                                uint64_t* op_full, uint64_t* op_empty, RingState& ro, int ops) {
     if constexpr (SI < S) {
-      const int q = tid & 7;                                      // 16-byte chunk (8 pixels) of the 64-pixel row
+      const int q = tid & 7, c0 = tid >> 3;
       mbar_wait(&op_empty[ro.s], ro.ph ^ 1);
       uint8_t* opb = op_base + ro.s * NB * BLK;
-#pragma unroll 1
-      for (int j = 0; j < NB; ++j) {
-        for (int c = tid >> 3; c < cv; c += 16) {
-          const uint4* src = reinterpret_cast<const uint4*>(rawr + j * raw_blk + c * RAW_SHIFT_ROW) + q;
-          const uint4 a = src[0], b = src[1], cc = src[2];        // pixels w0-8+8q .. w0+16+8q
-          *reinterpret_cast<uint4*>(opb + j * BLK + c * 128 + ((q ^ (c & 7)) << 4)) = shift_window<SI - S / 2>(a, b, cc);
-        }
+#pragma unroll
+      for (int i = 0; i < 2 * NB; ++i) {
+        const int j = i >> 1, c = c0 + 32 * (i & 1);
+        if (c < cv)
+          *reinterpret_cast<uint4*>(opb + j * BLK + c * 128 + ((q ^ (c & 7)) << 4)) = shift_window<SI - S / 2>(win[i]);
       }
       fence_proxy_async();            // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(&op_full[ro.s]);
       ro.next(ops);
-      ShiftRow<NB, S, SI + 1>::run(rawr, raw_blk, cv, tid, op_base, op_full, op_empty, ro, ops);
+      ShiftRow<NB, S, SI + 1>::stores(win, cv, tid, op_base, op_full, op_empty, ro, ops);
     }
+  }
+  static __device__ __forceinline__ void run(const uint8_t* rawr, int raw_blk, int cv, int tid, uint8_t* op_base,
+                                             uint64_t* op_full, uint64_t* op_empty, RingState& ro, int ops) {
+    static_assert(S / 2 <= 4, "filter width <= 9");
+    const int q = tid & 7, c0 = tid >> 3;
+    uint32_t win[2 * NB][8];
+#pragma unroll
+    for (int i = 0; i < 2 * NB; ++i) {
+      const int j = i >> 1, c = c0 + 32 * (i & 1);
+      if (c < cv) {   // warp-uniform: a warp holds 4 consecutive channels and cv is a multiple of 16
+        const uint8_t* row = rawr + j * raw_blk + c * RAW_SHIFT_ROW;        // pixels w0-8 .. w0+71, 160 bytes
+        const uint4 own = *reinterpret_cast<const uint4*>(row + 16 * (q + 1));
+        uint32_t lz = __shfl_up_sync(0xffffffffu, own.z, 1), lw = __shfl_up_sync(0xffffffffu, own.w, 1);
+        uint32_t rx = __shfl_down_sync(0xffffffffu, own.x, 1), ry = __shfl_down_sync(0xffffffffu, own.y, 1);
+        if (q == 0) { const uint2 h = *reinterpret_cast<const uint2*>(row + 8); lz = h.x; lw = h.y; }
+        if (q == 7) { const uint2 h = *reinterpret_cast<const uint2*>(row + 16 * 9); rx = h.x; ry = h.y; }
+        win[i][0] = lz; win[i][1] = lw; win[i][2] = own.x; win[i][3] = own.y;
+        win[i][4] = own.z; win[i][5] = own.w; win[i][6] = rx; win[i][7] = ry;
+      }
+    }
+    stores(win, cv, tid, op_base, op_full, op_empty, ro, ops);
   }
 };
 
@@ -136,9 +160,9 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     }
     for (int i = 0; i < MAXRING; ++i) {
       mbar_init(&raw_full[i], 1);
-      mbar_init(&raw_empty[i], SHIFT ? 128 : 1);   // shift path: released by the 128 shifter threads
+      mbar_init(&raw_empty[i], SHIFT ? SHIFT_THREADS : 1);   // shift path: released by the shifter threads
       mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
-      mbar_init(&op_full[i], 128); mbar_init(&op_empty[i], 1);
+      mbar_init(&op_full[i], SHIFT_THREADS); mbar_init(&op_empty[i], 1);
     }
     mbar_init(a_res_full, 1);
     fence_barrier_init();
@@ -156,41 +180,68 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
   const int w0 = tw_ * 64, h0 = th_ * NB;
 
   if (warp == 0) {
-    // ================= activation producer =================
+    // ================= TMA producer: activation row blocks + (streamed) weight blocks =================
+    // One thread issues both, INTERLEAVED: the TMA unit serves a CTA's requests in order, so a burst of all row
+    // blocks of the next chunk (80 KB) in front of the small per-tap weight loads starved the MMA of weights for
+    // ~2 us per chunk (r2 ncu: tensor pipe 24 %, L2->SM 4.4 TB/s).  Row blocks of chunk g+1 are therefore
+    // spread over the taps of chunk g, behind each tap's weight block.
     if (lane == 0) {
       tma_prefetch_desc(&tmap_x);
-      RingState rb;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        TAP_TILE_DECODE(t)
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&raw_empty[rb.s], rb.ph ^ 1);
-          mbar_arrive_expect_tx(&raw_full[rb.s], p.rows_raw * RAW_BLK);
-          uint8_t* dst = raw_base + rb.s * p.rows_raw * RAW_BLK;
-          for (int i = 0; i < p.rows_raw; ++i)
-            tma_load_4d(dst + i * RAW_BLK, &tmap_x, &raw_full[rb.s], w0 - (SHIFT ? 8 : 0), h0 - p.ph + i, kc * 64, n_);
-          rb.next(p.rawb);
-        }
-      }
-    }
-  } else if (warp == 10) {
-    // ================= weight producer =================
-    if (lane == 0) {
       tma_prefetch_desc(&tmap_w);
       if (p.a_resident) {
         mbar_arrive_expect_tx(a_res_full, taps * p.kchunks * p.mrows * 128);
         for (int tap = 0; tap < taps; ++tap)
           for (int kc = 0; kc < p.kchunks; ++kc)
             tma_load_2d(a_base + (tap * p.kchunks + kc) * p.a_blk, &tmap_w, a_res_full, kc * 64, tap * p.Mpad);
-      } else {
-        RingState ra;
-        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x)
-          for (int kc = 0; kc < p.kchunks; ++kc)
-            for (int tap = 0; tap < taps; ++tap) {
-              mbar_wait(&a_empty[ra.s], ra.ph ^ 1);
-              mbar_arrive_expect_tx(&a_full[ra.s], p.mrows * 128);
-              tma_load_2d(a_base + ra.s * p.a_blk, &tmap_w, &a_full[ra.s], kc * 64, tap * p.Mpad);
-              ra.next(p.ast);
+      }
+      RingState rb, ra;
+      const int xoff = SHIFT ? 8 : 0;
+      int ct = blockIdx.x, ckc = 0;                       // current chunk (tile, channel chunk)
+      if (ct < p.num_tiles) {                             // its row blocks: all at once (nothing to overlap with yet)
+        TAP_TILE_DECODE(ct)
+        mbar_wait(&raw_empty[rb.s], rb.ph ^ 1);
+        mbar_arrive_expect_tx(&raw_full[rb.s], p.rows_raw * RAW_BLK);
+        for (int i = 0; i < p.rows_raw; ++i)
+          tma_load_4d(raw_base + (rb.s * p.rows_raw + i) * RAW_BLK, &tmap_x, &raw_full[rb.s], w0 - xoff, h0 - p.ph + i, 0, n_);
+        rb.next(p.rawb);
+      }
+      while (ct < p.num_tiles) {
+        int nt = ct, nkc = ckc + 1;                       // next chunk
+        if (nkc == p.kchunks) { nkc = 0; nt = ct + gridDim.x; }
+        const bool has_next = nt < p.num_tiles;
+        TAP_TILE_DECODE(has_next ? nt : ct)
+        uint8_t* dst = raw_base + rb.s * p.rows_raw * RAW_BLK;
+        bool armed = false;
+        int row = 0;
+        for (int tap = 0; tap < taps; ++tap) {
+          if (!p.a_resident) {
+            mbar_wait(&a_empty[ra.s], ra.ph ^ 1);
+            mbar_arrive_expect_tx(&a_full[ra.s], p.mrows * 128);
+            tma_load_2d(a_base + ra.s * p.a_blk, &tmap_w, &a_full[ra.s], ckc * 64, tap * p.Mpad);
+            ra.next(p.ast);
+          }
+          if (has_next) {
+            if (!armed && mbar_test_wait(&raw_empty[rb.s], rb.ph ^ 1)) {
+              mbar_arrive_expect_tx(&raw_full[rb.s], p.rows_raw * RAW_BLK);
+              armed = true;
             }
+            if (armed) {
+              const int quota = ((tap + 1) * p.rows_raw + taps - 1) / taps;
+              for (; row < quota; ++row)
+                tma_load_4d(dst + row * RAW_BLK, &tmap_x, &raw_full[rb.s], w0 - xoff, h0 - p.ph + row, nkc * 64, n_);
+            }
+          }
+        }
+        if (has_next) {
+          if (!armed) {
+            mbar_wait(&raw_empty[rb.s], rb.ph ^ 1);
+            mbar_arrive_expect_tx(&raw_full[rb.s], p.rows_raw * RAW_BLK);
+          }
+          for (; row < p.rows_raw; ++row)
+            tma_load_4d(dst + row * RAW_BLK, &tmap_x, &raw_full[rb.s], w0 - xoff, h0 - p.ph + row, nkc * 64, n_);
+          rb.next(p.rawb);
+        }
+        ct = nt; ckc = nkc;
       }
     }
   } else if (warp == 1) {
@@ -238,10 +289,10 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         if (++acc == 2) { acc = 0; aph ^= 1; }
       }
     }
-  } else if (warp >= 6 && warp <= 9) {
+  } else if (warp >= 6) {
     // ================= shifter: raw row blocks -> swizzled operand tile of tap (r, s) =================
     if (SHIFT) {
-      const int tid = threadIdx.x - 6 * 32;   // 0..127
+      const int tid = threadIdx.x - 6 * 32;   // 0..255
       RingState rb, ro;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -250,7 +301,7 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
           const uint8_t* rawb = raw_base + rb.s * p.rows_raw * RAW_BLK;
           for (int r = 0; r < p.R; ++r)
             ShiftRow<NB, S, 0>::run(rawb + r * RAW_BLK, RAW_BLK, cv, tid, op_base, op_full, op_empty, ro, p.ops);
-          mbar_arrive(&raw_empty[rb.s]);      // all 128 shifter threads are done reading this raw buffer
+          mbar_arrive(&raw_empty[rb.s]);      // all shifter threads are done reading this raw buffer
           rb.next(p.rawb);
         }
       }

@@ -60,16 +60,29 @@ def _pool(sp, kind, k, stride, padding):
     return Pool(operation=kind, kernel_size=k, stride=stride, padding=padding, count_include_pad=False, **sp)
 
 
-def _relu_conv_bn_chain(convs):
-    """[ReLU, conv, BN] per conv, flattened into one Sequential (indices 0,1,2, 3,4,5, ...)."""
+def _relu_conv_bn_chain(convs, fused=False):
+    """[ReLU, conv, BN] per conv, flattened into one Sequential (indices 0,1,2, 3,4,5, ...).  `fused` (cells of a
+    spatial stage): the same children and state-dict keys, but every BatchNorm2d runs fused with the ReLU that
+    follows it on libspconv (torchgems.fused.relu_conv_bn_chain)."""
     mods = []
     for c in convs:
         mods += [nn.ReLU(inplace=False), c, nn.BatchNorm2d(c.out_channels)]
+    if fused:
+        from ..torchgems.fused import relu_conv_bn_chain
+        return relu_conv_bn_chain(*mods)
     return nn.Sequential(*mods)
 
 
+def _bn(sp, bn, x):
+    """BatchNorm2d of a cell: fused statistics + apply on libspconv inside a spatial stage."""
+    if sp:
+        from ..torchgems.fused import bn_relu
+        return bn_relu(x, bn, relu=False)
+    return bn(x)
+
+
 def relu_conv_bn(sp, in_channels, out_channels, kernel_size=1, stride=1, padding=0):
-    return _relu_conv_bn_chain([_conv(sp, in_channels, out_channels, kernel_size, stride, padding)])
+    return _relu_conv_bn_chain([_conv(sp, in_channels, out_channels, kernel_size, stride, padding)], fused=sp is not None)
 
 
 class FactorizedReduce(nn.Module):
@@ -80,10 +93,11 @@ class FactorizedReduce(nn.Module):
         self.conv1 = _conv(None, in_channels, out_channels // 2, 1, 2, local=local)
         self.conv2 = _conv(None, in_channels, out_channels // 2, 1, 2, local=local)
         self.bn = nn.BatchNorm2d(out_channels)
+        self._fused = local
 
     def forward(self, x):
         x = self.relu(x)
-        return self.bn(torch.cat([self.conv1(x), self.conv2(x)], dim=1))
+        return _bn(self._fused, self.bn, torch.cat([self.conv1(x), self.conv2(x)], dim=1))
 
 
 def _make_op(name, sp, c, stride):
@@ -96,12 +110,13 @@ def _make_op(name, sp, c, stride):
     if name == "max_pool_2x2":
         return _pool(sp, "MaxPool2d", 2, stride, 0)
     if name == "conv_1x1":
-        return _relu_conv_bn_chain([_conv(None, c, c, 1, stride, local=loc)])
+        return _relu_conv_bn_chain([_conv(None, c, c, 1, stride, local=loc)], fused=loc)
     if name == "conv_3x3":
-        return _relu_conv_bn_chain([_conv(None, c, q, local=loc), _conv(sp, q, q, 3, stride, 1), _conv(None, q, c, local=loc)])
+        return _relu_conv_bn_chain([_conv(None, c, q, local=loc), _conv(sp, q, q, 3, stride, 1), _conv(None, q, c, local=loc)],
+                                   fused=loc)
     if name == "conv_1x7_7x1":
         return _relu_conv_bn_chain([_conv(sp, c, q), _conv(sp, q, q, (1, 7), (1, stride), (0, 3)),
-                                    _conv(sp, q, q, (7, 1), (stride, 1), (3, 0)), _conv(sp, q, c)])
+                                    _conv(sp, q, q, (7, 1), (stride, 1), (3, 0)), _conv(sp, q, c)], fused=loc)
     raise KeyError(name)
 
 
@@ -127,9 +142,10 @@ class Stem(nn.Module):
         self.conv = _conv(sp, 3, channels, 3, stride=2, padding=1)
         self.relu = nn.ReLU(inplace=False)
         self.bn = nn.BatchNorm2d(channels)
+        self._fused = sp is not None
 
     def forward(self, x):
-        return self.bn(self.conv(self.relu(x)))
+        return _bn(self._fused, self.bn, self.conv(self.relu(x)))
 
 
 class Cell(nn.Module):
