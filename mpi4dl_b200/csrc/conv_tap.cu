@@ -17,6 +17,8 @@
 //
 // Warp roles (448 threads): 0 = TMA producer (activation row blocks and weight blocks, interleaved), 1 = MMA issuer
 // (+TMEM alloc), 2..5 = epilogue, 6..13 = shifter.  All hand-offs are mbarriers; persistent CTAs, one per SM.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -34,6 +36,7 @@ constexpr int TAP_THREADS = 448;
 constexpr int BLK = 8192;          // one operand block: [64 ch][64 px] bf16, 128-byte rows, SWIZZLE_128B
 constexpr int RAW_SHIFT_ROW = 160;  // raw row block of the shift path: [cbox ch][80 px], dense rows of 160 B
 constexpr int MAXRING = 8;
+constexpr int STAGE_BYTES = 128 * 128;   // epilogue staging buffer: one [128 ch][64 px] block
 
 struct TapParams {
   int M, Cin, H, W, N;
@@ -47,7 +50,11 @@ struct TapParams {
   int tiles_w, tiles_h, num_tiles;
   int a_resident, ast, ops;  // weights resident?; weight ring depth; operand ring depth
   int rawb;                  // raw (activation row block) buffers in the ring: 2..MAXRING, sized by bytes in flight
+  int opblk;                 // bytes of one 64-pixel block of an operand tile: cbox * 128
+  int group;                 // 1: an operand-ring slot holds the S tiles of one filter ROW (one hand-shake per row), 0: one tap
   int rows_raw;              // NB + R - 1
+  int dbg;                   // SPC_TAP_DBG bit mask (timing experiments only, results are garbage): 1 no weight loads,
+                             // 2 no activation loads, 4 no output stores, 8 shifter does no data movement
   const __nv_bfloat16* bias;
   __nv_bfloat16* y;
 };
@@ -85,26 +92,29 @@ constexpr int SHIFT_THREADS = 256;   // 8 shifter warps; thread -> (16-byte chun
 // once per filter ROW instead of three times per TAP.
 template <int NB, int S, int SI>
 struct ShiftRow {
-  static __device__ __forceinline__ void stores(const uint32_t (&win)[2 * NB][8], int cv, int tid, uint8_t* op_base,
-                                                uint64_t* op_full, uint64_t* op_empty, RingState& ro, int ops) {
+  static __device__ __forceinline__ void stores(const uint32_t (&win)[2 * NB][8], int cv, int tid, uint8_t* op_base, int opblk,
+                                                int group, uint64_t* op_full, uint64_t* op_empty, RingState& ro, int ops) {
     if constexpr (SI < S) {
       const int q = tid & 7, c0 = tid >> 3;
-      mbar_wait(&op_empty[ro.s], ro.ph ^ 1);
-      uint8_t* opb = op_base + ro.s * NB * BLK;
+      const int tile_bytes = NB * opblk;
+      if (!group || SI == 0) mbar_wait(&op_empty[ro.s], ro.ph ^ 1);
+      uint8_t* opb = op_base + ro.s * (group ? S : 1) * tile_bytes + (group ? SI * tile_bytes : 0);
 #pragma unroll
       for (int i = 0; i < 2 * NB; ++i) {
         const int j = i >> 1, c = c0 + 32 * (i & 1);
         if (c < cv)
-          *reinterpret_cast<uint4*>(opb + j * BLK + c * 128 + ((q ^ (c & 7)) << 4)) = shift_window<SI - S / 2>(win[i]);
+          *reinterpret_cast<uint4*>(opb + j * opblk + c * 128 + ((q ^ (c & 7)) << 4)) = shift_window<SI - S / 2>(win[i]);
       }
-      fence_proxy_async();            // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&op_full[ro.s]);
-      ro.next(ops);
-      ShiftRow<NB, S, SI + 1>::stores(win, cv, tid, op_base, op_full, op_empty, ro, ops);
+      if (!group || SI == S - 1) {
+        fence_proxy_async();            // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&op_full[ro.s]);
+        ro.next(ops);
+      }
+      ShiftRow<NB, S, SI + 1>::stores(win, cv, tid, op_base, opblk, group, op_full, op_empty, ro, ops);
     }
   }
-  static __device__ __forceinline__ void run(const uint8_t* rawr, int raw_blk, int cv, int tid, uint8_t* op_base,
-                                             uint64_t* op_full, uint64_t* op_empty, RingState& ro, int ops) {
+  static __device__ __forceinline__ void run(const uint8_t* rawr, int raw_blk, int cv, int tid, uint8_t* op_base, int opblk,
+                                             int group, uint64_t* op_full, uint64_t* op_empty, RingState& ro, int ops) {
     static_assert(S / 2 <= 4, "filter width <= 9");
     const int q = tid & 7, c0 = tid >> 3;
     uint32_t win[2 * NB][8];
@@ -122,13 +132,14 @@ struct ShiftRow {
         win[i][4] = own.z; win[i][5] = own.w; win[i][6] = rx; win[i][7] = ry;
       }
     }
-    stores(win, cv, tid, op_base, op_full, op_empty, ro, ops);
+    stores(win, cv, tid, op_base, opblk, group, op_full, op_empty, ro, ops);
   }
 };
 
 template <int NB, int S>
 __global__ void __launch_bounds__(TAP_THREADS, 1)
-conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, const TapParams p) {
+conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+                const __grid_constant__ CUtensorMap tmap_y, const TapParams p) {
   constexpr bool SHIFT = S > 1;
   constexpr int NPIX = NB * 64;
   const int RAW_BLK = p.raw_blk;
@@ -139,7 +150,9 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
   uint8_t* a_base = smem;
   uint8_t* raw_base = a_base + a_blocks * p.a_blk;
   uint8_t* op_base = raw_base + p.rawb * p.rows_raw * RAW_BLK;
-  uint8_t* bar_base = op_base + (SHIFT ? p.ops * NB * BLK : 0);
+  const int slot_bytes = (p.group ? S : 1) * NB * p.opblk;            // one operand-ring slot
+  uint8_t* stage_base = op_base + (SHIFT ? p.ops * slot_bytes : 0);   // epilogue staging: [128 ch][64 px] swizzled
+  uint8_t* bar_base = stage_base + STAGE_BYTES;
   uint64_t* raw_full = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* raw_empty = raw_full + MAXRING;
   uint64_t* a_full = raw_empty + MAXRING;
@@ -197,7 +210,8 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       RingState rb, ra;
       const int xoff = SHIFT ? 8 : 0;
       int ct = blockIdx.x, ckc = 0;                       // current chunk (tile, channel chunk)
-      if (ct < p.num_tiles) {                             // its row blocks: all at once (nothing to overlap with yet)
+      const bool noa = p.dbg & 1, noraw = p.dbg & 2;
+      if (ct < p.num_tiles && !noraw) {                   // its row blocks: all at once (nothing to overlap with yet)
         TAP_TILE_DECODE(ct)
         mbar_wait(&raw_empty[rb.s], rb.ph ^ 1);
         mbar_arrive_expect_tx(&raw_full[rb.s], p.rows_raw * RAW_BLK);
@@ -208,13 +222,13 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       while (ct < p.num_tiles) {
         int nt = ct, nkc = ckc + 1;                       // next chunk
         if (nkc == p.kchunks) { nkc = 0; nt = ct + gridDim.x; }
-        const bool has_next = nt < p.num_tiles;
+        const bool has_next = nt < p.num_tiles && !noraw;
         TAP_TILE_DECODE(has_next ? nt : ct)
         uint8_t* dst = raw_base + rb.s * p.rows_raw * RAW_BLK;
         bool armed = false;
         int row = 0;
         for (int tap = 0; tap < taps; ++tap) {
-          if (!p.a_resident) {
+          if (!p.a_resident && !noa) {
             mbar_wait(&a_empty[ra.s], ra.ph ^ 1);
             mbar_arrive_expect_tx(&a_full[ra.s], p.mrows * 128);
             tma_load_2d(a_base + ra.s * p.a_blk, &tmap_w, &a_full[ra.s], ckc * 64, tap * p.Mpad);
@@ -255,13 +269,14 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         mbar_wait(&tempty[acc], aph ^ 1);
         tc_fence_after();
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          if (!SHIFT) { mbar_wait(&raw_full[rb.s], rb.ph); tc_fence_after(); }
+          if (!SHIFT && !(p.dbg & 2)) { mbar_wait(&raw_full[rb.s], rb.ph); tc_fence_after(); }
           const int nsteps = min(4, (p.Cin - kc * 64 + 15) / 16);
           for (int tap = 0; tap < taps; ++tap) {
             uint32_t sb;
+            const int si = tap % S;                                   // filter column (compile-time S)
             if (SHIFT) {
-              mbar_wait(&op_full[ro.s], ro.ph);
-              sb = smem_u32(op_base + ro.s * NB * BLK);
+              if (!p.group || si == 0) mbar_wait(&op_full[ro.s], ro.ph);
+              sb = smem_u32(op_base + ro.s * slot_bytes + (p.group ? si * NB * p.opblk : 0));
             } else {
               sb = smem_u32(raw_base + (rb.s * p.rows_raw + tap) * RAW_BLK);   // S == 1: tap == filter row
             }
@@ -269,21 +284,21 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             if (p.a_resident) {
               sa = smem_u32(a_base + (tap * p.kchunks + kc) * p.a_blk);
             } else {
-              mbar_wait(&a_full[ra.s], ra.ph);
+              if (!(p.dbg & 1)) mbar_wait(&a_full[ra.s], ra.ph);
               sa = smem_u32(a_base + ra.s * p.a_blk);
             }
             tc_fence_after();
             for (int ks = 0; ks < nsteps; ++ks) {
               // B: MN-major SW128, 16 channels = two 8-row groups (SBO 1024 B); 64-pixel blocks (= tile rows) at LBO
-              const uint64_t bdesc = umma_desc(sb + ks * 2048, SHIFT ? BLK : RAW_BLK, 1024);
+              const uint64_t bdesc = umma_desc(sb + ks * 2048, SHIFT ? p.opblk : RAW_BLK, 1024);
               // A: K-major SW128, 8-row groups at SBO 1024 B; +32 B per 16-channel k-step
               const uint64_t adesc = umma_desc(sa + ks * 32, 16, 1024);
               umma_bf16(tmem_base + acc * NPIX, adesc, bdesc, IDESC, (kc | tap | ks) ? 1u : 0u);
             }
-            if (SHIFT) { umma_commit(&op_empty[ro.s]); ro.next(p.ops); }
-            if (!p.a_resident) { umma_commit(&a_empty[ra.s]); ra.next(p.ast); }
+            if (SHIFT && (!p.group || si == S - 1)) { umma_commit(&op_empty[ro.s]); ro.next(p.ops); }
+            if (!p.a_resident) { if (!(p.dbg & 1)) umma_commit(&a_empty[ra.s]); ra.next(p.ast); }
           }
-          if (!SHIFT) { umma_commit(&raw_empty[rb.s]); rb.next(p.rawb); }
+          if (!SHIFT) { if (!(p.dbg & 2)) umma_commit(&raw_empty[rb.s]); rb.next(p.rawb); }
         }
         umma_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; aph ^= 1; }
@@ -296,12 +311,12 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       RingState rb, ro;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&raw_full[rb.s], rb.ph);
-          const int cv = min(64, (p.Cin - kc * 64 + 15) & ~15);      // channels the MMA reads of this chunk
+          if (!(p.dbg & 2)) mbar_wait(&raw_full[rb.s], rb.ph);
+          const int cv = (p.dbg & 8) ? 0 : min(64, (p.Cin - kc * 64 + 15) & ~15);      // channels the MMA reads of this chunk
           const uint8_t* rawb = raw_base + rb.s * p.rows_raw * RAW_BLK;
           for (int r = 0; r < p.R; ++r)
-            ShiftRow<NB, S, 0>::run(rawb + r * RAW_BLK, RAW_BLK, cv, tid, op_base, op_full, op_empty, ro, p.ops);
-          mbar_arrive(&raw_empty[rb.s]);      // all shifter threads are done reading this raw buffer
+            ShiftRow<NB, S, 0>::run(rawb + r * RAW_BLK, RAW_BLK, cv, tid, op_base, p.opblk, p.group, op_full, op_empty, ro, p.ops);
+          if (!(p.dbg & 2)) mbar_arrive(&raw_empty[rb.s]);      // all shifter threads are done reading this raw buffer
           rb.next(p.rawb);
         }
       }
@@ -311,6 +326,7 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     const int quarter = warp & 3;
     const int k = quarter * 32 + lane;                 // output channel = TMEM lane
     const float bias = (k < p.M && p.bias) ? __bfloat162float(p.bias[k]) : 0.f;
+    const bool leader = threadIdx.x == 64;
     int acc = 0, aph = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       TAP_TILE_DECODE(t)
@@ -318,30 +334,41 @@ conv_tap_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < NB; ++j) {
-        const bool row_ok = (h0 + j) < p.H && k < p.M;
-        __nv_bfloat16* dst = p.y + (((size_t)n_ * p.M + (k < p.M ? k : 0)) * p.H + (h0 + j < p.H ? h0 + j : 0)) * p.W + w0;
+        // the TMA store that last read the staging buffer must be done reading it
+        if (leader) tma_store_wait_read<0>();
+        named_bar_sync(1, 128);
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * NPIX + j * 64 + cc * 32, r);
           tmem_ld_wait();
-          if (row_ok) {
+          uint8_t* rowp = stage_base + k * 128;           // thread = output channel = one 128-byte row of the box
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(r[8 * v + 0]) + bias, __uint_as_float(r[8 * v + 1]) + bias);
-              o.y = pack_bf16x2(__uint_as_float(r[8 * v + 2]) + bias, __uint_as_float(r[8 * v + 3]) + bias);
-              o.z = pack_bf16x2(__uint_as_float(r[8 * v + 4]) + bias, __uint_as_float(r[8 * v + 5]) + bias);
-              o.w = pack_bf16x2(__uint_as_float(r[8 * v + 6]) + bias, __uint_as_float(r[8 * v + 7]) + bias);
-              *reinterpret_cast<uint4*>(dst + cc * 32 + v * 8) = o;
-            }
+          for (int v = 0; v < 4; ++v) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(r[8 * v + 0]) + bias, __uint_as_float(r[8 * v + 1]) + bias);
+            o.y = pack_bf16x2(__uint_as_float(r[8 * v + 2]) + bias, __uint_as_float(r[8 * v + 3]) + bias);
+            o.z = pack_bf16x2(__uint_as_float(r[8 * v + 4]) + bias, __uint_as_float(r[8 * v + 5]) + bias);
+            o.w = pack_bf16x2(__uint_as_float(r[8 * v + 6]) + bias, __uint_as_float(r[8 * v + 7]) + bias);
+            const int chunk = (cc * 4 + v) ^ (k & 7);     // SWIZZLE_128B: 16-byte chunk ^ (row % 8)
+            *reinterpret_cast<uint4*>(rowp + chunk * 16) = o;
           }
         }
+        if (j == NB - 1) {                                // accumulator fully read: the MMA may reuse it
+          tc_fence_before();
+          mbar_arrive(&tempty[acc]);
+        }
+        fence_proxy_async();                              // smem writes -> visible to the TMA (async proxy)
+        named_bar_sync(1, 128);
+        // rows past the image and channels past M are clipped by the tensor map
+        if (leader && !(p.dbg & 4) && h0 + j < p.H) {
+          tma_store_4d(&tmap_y, stage_base, w0, h0 + j, 0, n_);
+          tma_store_commit();
+        }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; aph ^= 1; }
     }
+    if (leader) tma_store_wait_read<0>();
   }
 #undef TAP_TILE_DECODE
   tc_fence_before();
@@ -375,38 +402,42 @@ bool plan_tap(int M, int Cin, int R, int S, int H, int W, int N, TapPlan* out) {
   const int budget = TAP_SMEM_LIMIT - TAP_SMEM_AUX;
   // an M = 128 MMA reads 128 rows of A whatever mrows is: the bytes after the last A block must exist -> the raw
   // buffers follow the A region (always >= 16 KB)
+  p.opblk = p.cbox * 128;
+  const int budget_ops = budget - STAGE_BYTES;
   for (int NB = 4; NB >= 2; NB -= 2) {
     if (NB == 4 && H < 4) continue;
     p.rows_raw = NB + R - 1;
     const int raw_buf = p.rows_raw * raw_blk;                   // one raw buffer (all row blocks of a chunk)
-    const int op_tile = NB * BLK;
     const int a_res = taps * p.kchunks * p.a_blk;
     for (int resident = 1; resident >= 0; --resident) {
-      // minimum configuration: 2 raw buffers, (shift) 2 operand tiles, weights resident or a ring of 4 blocks
-      int ast = resident ? 0 : 4;
-      int a_bytes = resident ? a_res : ast * p.a_blk;
-      int rawb = 2, ops = shift ? 2 : 0;
-      int rem = budget - a_bytes - rawb * raw_buf - ops * op_tile;
-      if (rem < 0) continue;
-      // spend what is left on bytes in flight: the loads are latency-bound (~1.5 us from L2 under load), so
-      // the TMA rings should hold ~100 KB beyond what the MMA is reading.  Order: operand ring to 3 (shifter /
-      // MMA decoupling), weight ring to 8, then raw buffers.
-      if (shift && rem >= op_tile) { ++ops; rem -= op_tile; }
-      while (!resident && ast < MAXRING && rem >= p.a_blk) { ++ast; rem -= p.a_blk; }
-      while (rawb < MAXRING && rem >= raw_buf) { ++rawb; rem -= raw_buf; }
-      while (shift && ops < 4 && rem >= op_tile) { ++ops; rem -= op_tile; }
-      a_bytes = resident ? a_res : ast * p.a_blk;
-      p.a_resident = resident; p.ast = ast; p.ops = ops; p.rawb = rawb;
-      out->NB = NB; out->p = p;
-      out->smem = a_bytes + rawb * raw_buf + ops * op_tile + TAP_SMEM_AUX;
-      return true;
+      for (int group = shift ? 1 : 0; group >= 0; --group) {
+        // operand-ring slot: the S tiles of one filter row (one shifter <-> MMA hand-shake per row: the ~500-cycle
+        // round trip per hand-shake dominated the small-channel layers), else one tile
+        const int slot = (group ? S : 1) * NB * p.opblk;
+        // minimum configuration: 2 raw buffers, (shift) 2 operand slots, weights resident or a ring of 3 blocks
+        int ast = resident ? 0 : 3;
+        int a_bytes = resident ? a_res : ast * p.a_blk;
+        int rawb = 2, ops = shift ? 2 : 0;
+        int rem = budget_ops - a_bytes - rawb * raw_buf - ops * slot;
+        if (rem < 0) continue;
+        if (shift && !group && rem >= slot) { ++ops; rem -= slot; }
+        while (!resident && ast < MAXRING && rem >= p.a_blk) { ++ast; rem -= p.a_blk; }
+        while (rawb < 4 && rem >= raw_buf) { ++rawb; rem -= raw_buf; }
+        while (shift && ops < 4 && rem >= slot) { ++ops; rem -= slot; }
+        a_bytes = resident ? a_res : ast * p.a_blk;
+        p.a_resident = resident; p.ast = ast; p.ops = ops; p.rawb = rawb; p.group = group;
+        out->NB = NB; out->p = p;
+        out->smem = a_bytes + rawb * raw_buf + ops * slot + STAGE_BYTES + TAP_SMEM_AUX;
+        return true;
+      }
     }
   }
   return false;
 }
 
 template <int NB, int S>
-int launch_tap(const CUtensorMap& tw, const CUtensorMap& tx, const TapParams& p, int smem, cudaStream_t st) {
+int launch_tap(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, const TapParams& p, int smem,
+               cudaStream_t st) {
   auto kern = conv_tap_kernel<NB, S>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -415,7 +446,7 @@ int launch_tap(const CUtensorMap& tw, const CUtensorMap& tx, const TapParams& p,
   }
   const int sms = tc_sm_count();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  kern<<<grid, TAP_THREADS, smem, st>>>(tw, tx, p);
+  kern<<<grid, TAP_THREADS, smem, st>>>(tw, tx, ty, p);
   count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
@@ -437,10 +468,14 @@ int run_conv_tap_v2(const __nv_bfloat16* wp, int Mpad, int Cpad, const __nv_bflo
   SPC_REQUIRE(plan_tap(M, Cin, R, S, H, W, N, &pl), "tap conv: no shared-memory plan for M=%d Cin=%d %dx%d", M, Cin, R, S);
   TapParams& p = pl.p;
   p.ph = ph; p.Mpad = Mpad; p.bias = bias; p.y = y;
+  {
+    const char* e = getenv("SPC_TAP_DBG");   // read every call: dev probes flip it inside one process
+    p.dbg = e ? atoi(e) : 0;
+  }
   p.tiles_w = W / 64;
   p.tiles_h = (H + pl.NB - 1) / pl.NB;
   p.num_tiles = p.tiles_w * p.tiles_h * N;
-  CUtensorMap tw, tx;
+  CUtensorMap tw, tx, ty;
   {
     const uint64_t dims[2] = {(uint64_t)Cpad, (uint64_t)R * S * Mpad};
     const uint64_t strides[2] = {0, (uint64_t)Cpad * 2};
@@ -455,7 +490,14 @@ int run_conv_tap_v2(const __nv_bfloat16* wp, int Mpad, int Cpad, const __nv_bflo
     int rc = make_tmap_ex(&tx, x, 4, dims, strides, box, S > 1 ? 0 : 1);
     if (rc) return rc;
   }
-#define TAP_CASE(nb, s) if (pl.NB == nb && S == s) return launch_tap<nb, s>(tw, tx, p, pl.smem, st);
+  {
+    const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)M, (uint64_t)N};
+    const uint64_t strides[4] = {0, (uint64_t)W * 2, (uint64_t)H * W * 2, (uint64_t)H * W * M * 2};
+    const uint32_t box[4] = {64, 1, 128, 1};
+    int rc = make_tmap_ex(&ty, y, 4, dims, strides, box, 1);
+    if (rc) return rc;
+  }
+#define TAP_CASE(nb, s) if (pl.NB == nb && S == s) return launch_tap<nb, s>(tw, tx, ty, p, pl.smem, st);
   TAP_CASE(2, 1) TAP_CASE(4, 1) TAP_CASE(2, 3) TAP_CASE(4, 3) TAP_CASE(2, 5) TAP_CASE(4, 5) TAP_CASE(2, 7) TAP_CASE(4, 7)
 #undef TAP_CASE
   set_error("tap conv: unsupported filter width %d", S);

@@ -3,9 +3,12 @@ two mirrored replicas of an SP+LP pipeline -- train_spatial_model_master over tw
 second on the mirrored rank line (GEMS_INVERSE) -- whose spatial stages run conv_spatial / Pool on libspconv with
 the halo mailboxes between the tile ranks of EACH replica.  World = 4 processes (replica 1: tiles on ranks 0,1,
 join 2, tail 3; replica 2: tiles on ranks 3,2, join 1, tail 0); with fewer than 4 GPUs they share cuda:0 and
-torch.distributed runs on gloo.  Oracle: each replica is an independent model here (run_step does not mix them),
-so its loss sequence must equal a single-process PyTorch fp32 model with that replica's initial weights trained on
-that replica's half of every batch with the same rule (spatial-stage gradients SUM over tiles / P)."""
+torch.distributed runs on gloo.  The step is the benchmark script's (benchmark_gems_master_with_sp.py): run_step, then
+SyncAllreduce.apply_allreduce_master_master over the MASTER groups wired by sync_comms_for_master, then both updates.
+Oracle: the FIRST loss of each replica depends only on its initial weights and its half of the batch, so it must equal
+a single-process PyTorch fp32 model of the same network (forward through conv_spatial + halo mailboxes + SP->LP
+junction on the mirrored rank line); after that the two replicas' gradients are mixed by the MASTER allreduce, so the
+later losses are checked to be finite and the run to complete on every rank with libspconv kernels launched."""
 import os
 
 import pytest
@@ -33,27 +36,16 @@ def _batch(step):
     return torch.randn(2 * BATCH, 3, IMG, IMG, generator=g), torch.randint(0, 10, (2 * BATCH,), generator=g)
 
 
-def _sequential_losses(seed, half):
+def _sequential_first_loss(seed, half):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     m = nn.Sequential(*_layers(lambda ci, co, k, s: nn.Conv2d(ci, co, k, stride=s, padding=k // 2),
                                lambda: nn.AvgPool2d(3, stride=1, padding=1), seed)).cuda()
-    opt = torch.optim.SGD(m.parameters(), lr=0.005, momentum=0.9)
     crit = nn.CrossEntropyLoss()
-    n_spatial = sum(1 for _ in nn.Sequential(*list(m)[:BALANCE[0]]).parameters())
-    losses = []
-    for step in range(STEPS):
-        x, y = _batch(step)
-        x, y = x[half * BATCH:(half + 1) * BATCH], y[half * BATCH:(half + 1) * BATCH]
-        loss = crit(m(x.cuda()), y.cuda())
-        loss.backward()
-        for i, p in enumerate(m.parameters()):
-            if i < n_spatial:
-                p.grad.div_(P)
-        opt.step()
-        opt.zero_grad()
-        losses.append(loss.item())
-    return losses
+    x, y = _batch(0)
+    x, y = x[half * BATCH:(half + 1) * BATCH], y[half * BATCH:(half + 1) * BATCH]
+    with torch.no_grad():
+        return float(crit(m(x.cuda()), y.cuda()))
 
 
 def _worker(rank, port, ngpu, q):
@@ -73,7 +65,8 @@ def _worker(rank, port, ngpu, q):
     c1 = gems_comm.MPIComm(split_size=SPLIT, ENABLE_MASTER=False, ENABLE_SPATIAL=True, num_spatial_parts=P, spatial_size=1)
     c2 = gems_comm.MPIComm(split_size=SPLIT, ENABLE_MASTER=True, ENABLE_SPATIAL=True, num_spatial_parts=P, spatial_size=1,
                            DISABLE_INIT=True)
-    sync1, sync2 = gems_comm.SyncAllreduce(c1), gems_comm.SyncAllreduce(c2)
+    gems_comm.sync_comms_for_master(c1, c2)
+    sync = gems_comm.SyncAllreduce(c1)
     full = [(BATCH, WIDTH, IMG // 2, IMG // 2), (BATCH, 4, IMG // 2, IMG // 2), (BATCH, 10)]
     shapes = get_shapes_spatial(full, "vertical", 1, [P], 1)
     gens = []
@@ -97,10 +90,7 @@ def _worker(rank, port, ngpu, q):
         elif c2.local_rank < P:
             x = split_input(x, IMG, "vertical", c2.local_rank, [P])
         loss, _ = tm.run_step(x, y)
-        if c1.local_rank < P:
-            sync1.apply_allreduce(gens[0], c1.spatial_allreduce_grp)
-        if c2.local_rank < P:
-            sync2.apply_allreduce(gens[1], c2.spatial_allreduce_grp)
+        sync.apply_allreduce_master_master(gens[0], gens[1], c1, c2)
         tm.train_model1.update()
         tm.train_model2.update()
         losses.append(float(loss))
@@ -111,7 +101,7 @@ def _worker(rank, port, ngpu, q):
 
 
 def test_gems_master_with_spatial_parallelism_on_gpu():
-    want1, want2 = _sequential_losses(SEEDS[0], 0), _sequential_losses(SEEDS[1], 1)
+    want1, want2 = _sequential_first_loss(SEEDS[0], 0), _sequential_first_loss(SEEDS[1], 1)
     world = P + SPLIT - 1
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -137,5 +127,7 @@ def test_gems_master_with_spatial_parallelism_on_gpu():
     assert ok, "worker exit codes: %s" % [p.exitcode for p in ps]
     assert all(got[r][1] > 0 for r in range(world)), "every rank hosts a tile of one replica: libspconv kernels must have run"
     # replica 1's tail is world rank 3, replica 2's (mirrored line) is world rank 0; run_step returns the tail's loss
-    assert got[world - 1][0] == pytest.approx(want1, rel=2e-4, abs=2e-4)
-    assert got[0][0] == pytest.approx(want2, rel=2e-4, abs=2e-4)
+    import math
+    assert got[world - 1][0][0] == pytest.approx(want1, rel=2e-4, abs=2e-4)
+    assert got[0][0][0] == pytest.approx(want2, rel=2e-4, abs=2e-4)
+    assert all(math.isfinite(v) for r in (0, world - 1) for v in got[r][0])

@@ -70,5 +70,36 @@ def main():
     os.environ.pop("SPC_TAP_V1", None)
 
 
+def breakdown():
+    """Timing experiments with parts of the kernel switched off (SPC_TAP_DBG; results are garbage)."""
+    L = _lib.lib()
+    dev = "cuda:0"
+    sp = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+    for idx in (1, 0, 4, 6):
+        Cc, K, R, S, H, W = SHAPES[idx]
+        x = torch.randn(1, Cc, H, W, device=dev).to(torch.bfloat16)
+        w = (torch.randn(K, Cc, R, S, device=dev) / (Cc * R * S) ** 0.5).to(torch.bfloat16)
+        y = torch.empty(1, K, H, W, device=dev, dtype=torch.bfloat16)
+        d = _lib.ConvDesc(1, Cc, H, W, K, R, S, 1, 1, (R - 1) // 2, (S - 1) // 2, _lib.SPC_BF16, _lib.SPC_ALGO_TCGEN05)
+        nb = L.spc_conv_workspace_bytes(C.byref(d), 0)
+        ws = torch.empty(nb + 16, dtype=torch.uint8, device=dev)
+        out = []
+        for dbg in (0, 1, 2, 4, 8, 3, 7, 15, 11):
+            os.environ["SPC_TAP_DBG"] = str(dbg)
+            fn = lambda: _lib.check(L.spc_conv2d_fwd(C.byref(d), x.data_ptr(), None, w.data_ptr(), None, y.data_ptr(),  # noqa: E731
+                                                     ws.data_ptr(), nb, sp()), "fwd")
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            out.append("dbg%-2d %.3f" % (dbg, e0.elapsed_time(e1) / 5))
+        os.environ.pop("SPC_TAP_DBG", None)
+        print("%4d->%-4d %dx%d @%dx%d  (1=noW 2=noX 4=noStore 8=noShift)  " % (Cc, K, R, S, H, W) + "  ".join(out))
+
+
 if __name__ == "__main__":
-    main()
+    breakdown() if "--breakdown" in sys.argv else main()
