@@ -27,6 +27,11 @@ bool tap_v2_supported(int M, int Cin, int R, int S, int H, int W, int N, int str
 int run_conv_tap_v2(const __nv_bfloat16* wp, int Mpad, int Cpad, const __nv_bfloat16* x, const __nv_bfloat16* bias,
                     __nv_bfloat16* y, int M, int Cin, int R, int S, int ph, int H, int W, int N, cudaStream_t st);
 
+// wgrad_tap.cu: wgrad of the stride-1 tap convolutions (<= 128 channels on both sides), shifts formed in smem
+bool wgrad_tap_supported(int K, int C, int R, int S, int H, int W, int stride);
+int run_wgrad_tap(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K, int C, int N, int H, int W, int R, int S,
+                  cudaStream_t st);
+
 namespace {
 
 constexpr int TC_THREADS = 192;
@@ -1263,6 +1268,8 @@ size_t tc_workspace_bytes(const spc_conv_desc* d, int op) {
   if (op != 2 && !env_get("SPC_TAP_V1") &&
       tap_v2_supported(op == 1 ? d->C : d->K, op == 1 ? d->K : d->C, d->R, d->S, d->H, d->W, d->N, cs))
     return b;               // conv_tap.cu forms the horizontal taps in shared memory: no copies
+  if (op == 2 && !env_get("SPC_TAP_V1") && wgrad_tap_supported(d->K, d->C, d->R, d->S, d->H, d->W, cs))
+    return b;               // wgrad_tap.cu likewise
   if (d->S > 1 || cs > 1)   // S column-shifted (stride 2: also subsampled) copies of the conv input
     b += align1k((size_t)d->S * d->N * (op == 1 ? d->K : d->C) * d->H * Wo * 2) + 2048;
   return b;
@@ -1357,6 +1364,8 @@ int tc_conv_wgrad(const spc_conv_desc* d, const void* x, const void* dy, float* 
   const __nv_bfloat16* dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
   if (d->R * d->S > 1) {
     const int cs = d->stride_h;
+    if (!env_get("SPC_TAP_V1") && wgrad_tap_supported(d->K, d->C, d->R, d->S, d->H, d->W, cs))
+      return run_wgrad_tap(xb, dyb, dw, d->K, d->C, d->N, d->H, d->W, d->R, d->S, st);
     const bool copies = d->S > 1 || cs > 1;
     if (copies) {
       SPC_REQUIRE(ws && ws_bytes >= tc_workspace_bytes(d, 2), "tcgen05 wgrad: workspace too small");

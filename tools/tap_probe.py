@@ -30,6 +30,7 @@ def main():
         w = (torch.randn(K, Cc, R, S, device=dev) / (Cc * R * S) ** 0.5).to(torch.bfloat16)
         y = torch.empty(1, K, H, W, device=dev, dtype=torch.bfloat16)
         dx = torch.empty_like(x)
+        dw = torch.empty(K, Cc, R, S, device=dev, dtype=torch.float32)
         d = _lib.ConvDesc(1, Cc, H, W, K, R, S, 1, 1, (R - 1) // 2, (S - 1) // 2, _lib.SPC_BF16, _lib.SPC_ALGO_TCGEN05)
         res = {}
         for mode in (("v2",) if only else ("v2", "v1")):
@@ -38,12 +39,14 @@ def main():
             else:
                 os.environ.pop("SPC_TAP_V1", None)
             L.spc_reload_env()
-            nb = max(L.spc_conv_workspace_bytes(C.byref(d), i) for i in range(2))
+            nb = max(L.spc_conv_workspace_bytes(C.byref(d), i) for i in range(3))
             ws = torch.empty(nb + 16, dtype=torch.uint8, device=dev)
             fns = {"fprop": lambda: _lib.check(L.spc_conv2d_fwd(C.byref(d), x.data_ptr(), None, w.data_ptr(), None, y.data_ptr(),
                                                                 ws.data_ptr(), nb, sp()), "fwd"),
                    "dgrad": lambda: _lib.check(L.spc_conv2d_dgrad(C.byref(d), gy.data_ptr(), w.data_ptr(), dx.data_ptr(),
-                                                                  ws.data_ptr(), nb, sp()), "dgrad")}
+                                                                  ws.data_ptr(), nb, sp()), "dgrad"),
+                   "wgrad": lambda: _lib.check(L.spc_conv2d_wgrad(C.byref(d), x.data_ptr(), None, gy.data_ptr(), dw.data_ptr(), None,
+                                                                  0, ws.data_ptr(), nb, sp()), "wgrad")}
             for nm, fn in fns.items():
                 fn()
                 torch.cuda.synchronize()
@@ -53,11 +56,11 @@ def main():
                     fn()
                 e1.record()
                 torch.cuda.synchronize()
-                res[(mode, nm)] = (e0.elapsed_time(e1) / 5, (y if nm == "fprop" else dx).float().clone())
+                res[(mode, nm)] = (e0.elapsed_time(e1) / 5, {"fprop": y, "dgrad": dx, "wgrad": dw}[nm].float().clone())
             del ws
         gb = (Cc + K) * H * W * 2 / 1e9
         tf = 2.0 * Cc * K * R * S * H * W / 1e12
-        for nm in ("fprop", "dgrad"):
+        for nm in ("fprop", "dgrad", "wgrad"):
             if only:
                 print("%4d->%-4d %dx%d @%dx%d %-5s  v2 %7.3f ms" % (Cc, K, R, S, H, W, nm, res[("v2", nm)][0]))
                 continue
