@@ -33,8 +33,9 @@ namespace {
 constexpr int WT_THREADS = 448;
 constexpr int SHIFT_THREADS = 256;
 constexpr int RAW_ROW = 160;       // raw Q row: [Qch][80 px], dense rows of 160 bytes
-constexpr int PS = 3;              // P row stages
-constexpr int MAXQ = 10;           // Q row ring slots (<= R + 2)
+constexpr int MAXP = 8;            // P row stages (ring depths are chosen by the launcher: bytes in flight)
+constexpr int MAXRAW = 8;          // raw Q row slots
+constexpr int MAXQ = 16;           // Q row ring slots
 
 struct WtParams {
   float* dw;
@@ -49,6 +50,9 @@ struct WtParams {
   // this launch's tap rectangle (a "pass"): filter rows [r0, r0 + nr), columns [s0, s0 + ns)
   int r0, nr, s0, ns;
   int rq;                      // Q row ring slots (>= nr + 1)
+  int psn, rawn;               // P row stages, raw Q row slots
+  int nbw;                     // 64-pixel blocks per strip row (strip width = 64 * nbw): rows of few channels are
+                               // small, and the TMA loads are latency-bound -> wider strips keep more bytes in flight
   int raw_bytes;               // raw Q row bytes: Qc16 * 160
   int strips, row_splits, rows_per_split, num_items;
 };
@@ -102,26 +106,29 @@ wgrad_tap_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
   constexpr bool SHIFT = S > 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int qrow_bytes = p.ns * p.qt_bytes;                 // all tiles of one Q row
+  const int qblk_bytes = p.ns * p.qt_bytes;                 // the shifted tiles of one 64-pixel block of a Q row
+  const int qrow_bytes = p.nbw * qblk_bytes;                // ... of a whole strip row
+  const int prow_bytes = p.nbw * p.p_blk;
+  const int rawrow_bytes = p.nbw * p.raw_bytes;
   uint8_t* p_base = smem;
-  uint8_t* qt_base = p_base + PS * p.p_blk;
+  uint8_t* qt_base = p_base + p.psn * prow_bytes;
   uint8_t* raw_base = qt_base + p.rq * qrow_bytes;
-  uint8_t* bar_base = raw_base + (SHIFT ? 2 * p.raw_bytes : 0);
+  uint8_t* bar_base = raw_base + (SHIFT ? p.rawn * rawrow_bytes : 0);
   uint64_t* p_full = reinterpret_cast<uint64_t*>(bar_base);
-  uint64_t* p_empty = p_full + PS;
-  uint64_t* qt_full = p_empty + PS;
+  uint64_t* p_empty = p_full + MAXP;
+  uint64_t* qt_full = p_empty + MAXP;
   uint64_t* qt_empty = qt_full + MAXQ;
   uint64_t* raw_full = qt_empty + MAXQ;
-  uint64_t* raw_empty = raw_full + 2;
-  uint64_t* tfull = raw_empty + 2;
+  uint64_t* raw_empty = raw_full + MAXRAW;
+  uint64_t* tfull = raw_empty + MAXRAW;
   uint64_t* tempty = tfull + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < PS; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 1); }
+    for (int i = 0; i < MAXP; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 1); }
     for (int i = 0; i < MAXQ; ++i) { mbar_init(&qt_full[i], SHIFT ? SHIFT_THREADS : 1); mbar_init(&qt_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], SHIFT_THREADS); }
+    for (int i = 0; i < MAXRAW; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], SHIFT_THREADS); }
     mbar_init(tfull, 1);
     mbar_init(tempty, 128);
     fence_barrier_init();
@@ -137,7 +144,7 @@ wgrad_tap_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
   const int sp_ = (it) % p.row_splits;                                            \
   const int strip_ = ((it) / p.row_splits) % p.strips;                            \
   const int n_ = (it) / (p.row_splits * p.strips);                                \
-  const int w0 = strip_ * 64;                                                     \
+  const int w0 = strip_ * 64 * p.nbw;                                             \
   const int ha = sp_ * p.rows_per_split, hb = min(p.H, ha + p.rows_per_split);    \
   const int rows = hb - ha;                                                       \
   const int q_first = ha + p.r0 - p.ph;   /* image row of Q ring row 0 */         \
@@ -154,24 +161,27 @@ wgrad_tap_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
         if (rows <= 0) continue;
         for (int i = 0; i < q_rows; ++i) {
           if (SHIFT) {
-            const int s = rr.slot(2);
-            mbar_wait(&raw_empty[s], rr.phase(2) ^ 1);
-            mbar_arrive_expect_tx(&raw_full[s], p.raw_bytes);
-            tma_load_4d(raw_base + s * p.raw_bytes, &tmap_q, &raw_full[s], w0 - 8, q_first + i, 0, n_);
+            const int s = rr.slot(p.rawn);
+            mbar_wait(&raw_empty[s], rr.phase(p.rawn) ^ 1);
+            mbar_arrive_expect_tx(&raw_full[s], rawrow_bytes);
+            for (int b = 0; b < p.nbw; ++b)
+              tma_load_4d(raw_base + s * rawrow_bytes + b * p.raw_bytes, &tmap_q, &raw_full[s], w0 + 64 * b - 8, q_first + i, 0, n_);
             ++rr.i;
           } else {
             const int s = qr.slot(p.rq);
             mbar_wait(&qt_empty[s], qr.phase(p.rq) ^ 1);
-            mbar_arrive_expect_tx(&qt_full[s], p.qt_bytes);
-            tma_load_4d(qt_base + s * qrow_bytes, &tmap_q, &qt_full[s], w0, q_first + i, 0, n_);
+            mbar_arrive_expect_tx(&qt_full[s], p.nbw * p.qt_bytes);
+            for (int b = 0; b < p.nbw; ++b)
+              tma_load_4d(qt_base + s * qrow_bytes + b * qblk_bytes, &tmap_q, &qt_full[s], w0 + 64 * b, q_first + i, 0, n_);
             ++qr.i;
           }
           if (i >= p.nr - 1) {     // P row of step j = i - (nr - 1)
             const int j = i - (p.nr - 1);
-            const int s = pr.slot(PS);
-            mbar_wait(&p_empty[s], pr.phase(PS) ^ 1);
-            mbar_arrive_expect_tx(&p_full[s], p.p_bytes);
-            tma_load_4d(p_base + s * p.p_blk, &tmap_p, &p_full[s], w0, ha + j, 0, n_);
+            const int s = pr.slot(p.psn);
+            mbar_wait(&p_empty[s], pr.phase(p.psn) ^ 1);
+            mbar_arrive_expect_tx(&p_full[s], p.nbw * p.p_bytes);
+            for (int b = 0; b < p.nbw; ++b)
+              tma_load_4d(p_base + s * prow_bytes + b * p.p_blk, &tmap_p, &p_full[s], w0 + 64 * b, ha + j, 0, n_);
             ++pr.i;
           }
         }
@@ -196,22 +206,24 @@ wgrad_tap_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
             const int g = qr.i + j + i;
             mbar_wait(&qt_full[g % p.rq], (g / p.rq) & 1);
           }
-          const int ps = pr.slot(PS);
-          mbar_wait(&p_full[ps], pr.phase(PS));
+          const int ps = pr.slot(p.psn);
+          mbar_wait(&p_full[ps], pr.phase(p.psn));
           tc_fence_after();
-          const uint32_t sa = smem_u32(p_base + ps * p.p_blk);
-          for (int r = 0; r < p.nr; ++r) {
-            const int g = qr.i + j + r;
-            const uint32_t sq = smem_u32(qt_base + (g % p.rq) * qrow_bytes);
-            for (int sg = 0; sg * ns_g < p.ns; ++sg) {
-              const int nsg = min(ns_g, p.ns - sg * ns_g);
-              const uint32_t idesc = umma_idesc_bf16(128, nsg * p.Qc16, 0, 0);
-              const uint32_t dcol = tmem_base + (uint32_t)((r * p.ns + sg * ns_g) * p.Qc16);
+          for (int b = 0; b < p.nbw; ++b) {
+            const uint32_t sa = smem_u32(p_base + ps * prow_bytes + b * p.p_blk);
+            for (int r = 0; r < p.nr; ++r) {
+              const int g = qr.i + j + r;
+              const uint32_t sq = smem_u32(qt_base + (g % p.rq) * qrow_bytes + b * qblk_bytes);
+              for (int sg = 0; sg * ns_g < p.ns; ++sg) {
+                const int nsg = min(ns_g, p.ns - sg * ns_g);
+                const uint32_t idesc = umma_idesc_bf16(128, nsg * p.Qc16, 0, 0);
+                const uint32_t dcol = tmem_base + (uint32_t)((r * p.ns + sg * ns_g) * p.Qc16);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {   // 64 pixels = 4 k-steps of 16; +32 bytes inside the 128-byte swizzle row
-                const uint64_t adesc = umma_desc(sa + ks * 32, 16, 1024);
-                const uint64_t bdesc = umma_desc(sq + sg * ns_g * p.qt_bytes + ks * 32, 16, 1024);
-                umma_bf16(dcol, adesc, bdesc, idesc, (j | ks) ? 1u : 0u);
+                for (int ks = 0; ks < 4; ++ks) {   // 64 pixels = 4 k-steps of 16; +32 bytes inside the 128-byte swizzle row
+                  const uint64_t adesc = umma_desc(sa + ks * 32, 16, 1024);
+                  const uint64_t bdesc = umma_desc(sq + sg * ns_g * p.qt_bytes + ks * 32, 16, 1024);
+                  umma_bf16(dcol, adesc, bdesc, idesc, (j | b | ks) ? 1u : 0u);
+                }
               }
             }
           }
@@ -237,29 +249,31 @@ wgrad_tap_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_consta
         (void)w0; (void)n_; (void)q_first;
         if (rows <= 0) continue;
         for (int i = 0; i < q_rows; ++i) {
-          const int rs = rr.slot(2);
-          mbar_wait(&raw_full[rs], rr.phase(2));
-          const uint8_t* raw = raw_base + rs * p.raw_bytes;
-          uint32_t win[4][8];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int c = c0 + 32 * k;
-            if (c < p.Qc16) {   // warp-uniform (4 consecutive channels per warp, Qc16 multiple of 16)
-              const uint8_t* row = raw + c * RAW_ROW;
-              const uint4 own = *reinterpret_cast<const uint4*>(row + 16 * (q + 1));
-              uint32_t lz = __shfl_up_sync(0xffffffffu, own.z, 1), lw = __shfl_up_sync(0xffffffffu, own.w, 1);
-              uint32_t rx = __shfl_down_sync(0xffffffffu, own.x, 1), ry = __shfl_down_sync(0xffffffffu, own.y, 1);
-              if (q == 0) { const uint2 h = *reinterpret_cast<const uint2*>(row + 8); lz = h.x; lw = h.y; }
-              if (q == 7) { const uint2 h = *reinterpret_cast<const uint2*>(row + 16 * 9); rx = h.x; ry = h.y; }
-              win[k][0] = lz; win[k][1] = lw; win[k][2] = own.x; win[k][3] = own.y;
-              win[k][4] = own.z; win[k][5] = own.w; win[k][6] = rx; win[k][7] = ry;
-            }
-          }
-          mbar_arrive(&raw_empty[rs]);       // the raw row is in registers
-          ++rr.i;
+          const int rs = rr.slot(p.rawn);
+          mbar_wait(&raw_full[rs], rr.phase(p.rawn));
           const int qs = qr.slot(p.rq);
-          mbar_wait(&qt_empty[qs], qr.phase(p.rq) ^ 1);
-          ShiftCols<S, 0>::run(win, p.Qc16, tid, qt_base + qs * qrow_bytes, p.qt_bytes, p.s0, p.ns);
+          for (int b = 0; b < p.nbw; ++b) {
+            const uint8_t* raw = raw_base + rs * rawrow_bytes + b * p.raw_bytes;
+            uint32_t win[4][8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c = c0 + 32 * k;
+              if (c < p.Qc16) {   // warp-uniform (4 consecutive channels per warp, Qc16 multiple of 16)
+                const uint8_t* row = raw + c * RAW_ROW;
+                const uint4 own = *reinterpret_cast<const uint4*>(row + 16 * (q + 1));
+                uint32_t lz = __shfl_up_sync(0xffffffffu, own.z, 1), lw = __shfl_up_sync(0xffffffffu, own.w, 1);
+                uint32_t rx = __shfl_down_sync(0xffffffffu, own.x, 1), ry = __shfl_down_sync(0xffffffffu, own.y, 1);
+                if (q == 0) { const uint2 h = *reinterpret_cast<const uint2*>(row + 8); lz = h.x; lw = h.y; }
+                if (q == 7) { const uint2 h = *reinterpret_cast<const uint2*>(row + 16 * 9); rx = h.x; ry = h.y; }
+                win[k][0] = lz; win[k][1] = lw; win[k][2] = own.x; win[k][3] = own.y;
+                win[k][4] = own.z; win[k][5] = own.w; win[k][6] = rx; win[k][7] = ry;
+              }
+            }
+            if (b == p.nbw - 1) mbar_arrive(&raw_empty[rs]);       // the whole raw row has been read
+            if (b == 0) mbar_wait(&qt_empty[qs], qr.phase(p.rq) ^ 1);
+            ShiftCols<S, 0>::run(win, p.Qc16, tid, qt_base + qs * qrow_bytes + b * qblk_bytes, p.qt_bytes, p.s0, p.ns);
+          }
+          ++rr.i;
           fence_proxy_async();
           mbar_arrive(&qt_full[qs]);
           ++qr.i;
@@ -352,7 +366,9 @@ int plan_passes(int R, int S, int Qc16, int (*rect)[4]) {
 
 bool wgrad_tap_supported(int K, int C, int R, int S, int H, int W, int stride) {
   if (stride != 1 || R * S == 1 || (W % 64) != 0 || H < 1) return false;
-  if (!(S == 1 || S == 3 || S == 5 || S == 7) || (R & 1) == 0 || R > 7) return false;
+  // S == 1 (7x1): no horizontal shift is needed and round 1's pw_wgrad_kernel (row-shifted TMA boxes, no copies) is
+  // 1.4x faster than the line buffer there (profiles/r2_tap_probe_v2d.txt) -- it keeps those shapes
+  if (!(S == 3 || S == 5 || S == 7) || (R & 1) == 0 || R > 7) return false;
   if (K > 128 || C > 128) return false;
   const int Qc16 = rup(K >= C ? C : K, 16);
   int rect[16][4];
@@ -393,16 +409,34 @@ int run_wgrad_tap(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, in
     if (rc) return rc;
   }
   const int sms = tc_sm_count();
-  p.strips = W / 64;
+  // few channels -> small rows -> wider strips (more bytes per ring slot)
+  p.nbw = 1;
+  {
+    const int rowb = rup(p.Pch, 8) * 128 + p.Qc16 * 128;
+    while (p.nbw < 4 && rowb * p.nbw < 12 * 1024 && W % (128 * p.nbw) == 0) p.nbw *= 2;
+  }
+  p.strips = W / (64 * p.nbw);
   for (int pi = 0; pi < npass; ++pi) {
     // mode B mirrors the tap indices: the rectangle is planned in the kernel's (mirrored) index space either way
     p.r0 = rect[pi][0]; p.nr = rect[pi][1]; p.s0 = rect[pi][2]; p.ns = rect[pi][3];
-    const int qrow_bytes = p.ns * p.qt_bytes;
-    const int fixed = PS * p.p_blk + (S > 1 ? 2 * p.raw_bytes : 0) + WT_SMEM_AUX;
-    p.rq = (WT_SMEM_LIMIT - fixed) / qrow_bytes;
-    if (p.rq > p.nr + 3) p.rq = p.nr + 3;
-    if (p.rq > MAXQ) p.rq = MAXQ;
-    SPC_REQUIRE(p.rq >= p.nr + 1, "wgrad_tap: shared memory too small (rows %d, %d bytes per row)", p.nr, qrow_bytes);
+    const int qrow_bytes = p.nbw * p.ns * p.qt_bytes, prow = p.nbw * p.p_blk, rawrow = S > 1 ? p.nbw * p.raw_bytes : 0;
+    // ring depths.  Rows of many channels (>= ~12 KB per strip row) keep enough bytes in flight with 3 P stages,
+    // 2 raw rows and nr + 3 shifted rows (measured: deeper rings cost 10 % there); small rows are latency-bound
+    // on the ~2 us L2 round trip of their TMA loads, so they take whatever depth fits.
+    const bool small_rows = prow + p.nbw * p.qt_bytes < 12 * 1024;
+    p.psn = 3; p.rawn = S > 1 ? 2 : 0; p.rq = p.nr + 1;
+    int rem = WT_SMEM_LIMIT - WT_SMEM_AUX - p.psn * prow - p.rawn * rawrow - p.rq * qrow_bytes;
+    SPC_REQUIRE(rem >= 0, "wgrad_tap: shared memory too small (rows %d, %d bytes per row)", p.nr, qrow_bytes);
+    if (small_rows) {
+      for (bool grew = true; grew;) {
+        grew = false;
+        if (S > 1 && p.rawn < MAXRAW && rem >= rawrow) { ++p.rawn; rem -= rawrow; grew = true; }
+        if (p.psn < MAXP && rem >= prow) { ++p.psn; rem -= prow; grew = true; }
+        if (p.rq < MAXQ && p.rq < p.nr + 8 && rem >= qrow_bytes) { ++p.rq; rem -= qrow_bytes; grew = true; }
+      }
+    } else {
+      while (p.rq < p.nr + 3 && p.rq < MAXQ && rem >= qrow_bytes) { ++p.rq; rem -= qrow_bytes; }
+    }
     // row splits: fill the persistent grid with whole waves of (image, strip, row range) items
     const int base_items = N * p.strips;
     int best = 1;
@@ -416,7 +450,7 @@ int run_wgrad_tap(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, in
     p.row_splits = best;
     p.rows_per_split = (H + best - 1) / best;
     p.num_items = base_items * best;
-    const int smem = PS * p.p_blk + p.rq * qrow_bytes + (S > 1 ? 2 * p.raw_bytes : 0) + WT_SMEM_AUX;
+    const int smem = p.psn * prow + p.rq * qrow_bytes + p.rawn * rawrow + WT_SMEM_AUX;
     int rc;
     if (S == 1) rc = launch_wt<1>(tp, tq, p, smem, st);
     else if (S == 3) rc = launch_wt<3>(tp, tq, p, smem, st);
