@@ -744,7 +744,16 @@ def main():
         }
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
-        dist.destroy_process_group()
+        # tear down in order: captured graphs hold NCCL kernels; destroying the communicator under them hung the
+        # process at exit (r2, N=2: JSON printed, exit only by timeout)
+        dist.barrier()
+        torch.cuda.synchronize()
+        graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

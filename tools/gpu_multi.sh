@@ -8,21 +8,25 @@ mkdir -p gpurun_out profiles
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 echo "== halo sweep P=$N"
-timeout 300 $TR --nproc-per-node $N --master-port 29701 benchmarks/communication/halo/halo_sweep.py --reference-point \
+SW="--tiles 2048 4096 8192 16384"; [ "$N" = "8" ] && SW="--tiles 2048 8192 --slice-methods vertical"
+timeout 300 $TR --nproc-per-node $N --master-port 29701 benchmarks/communication/halo/halo_sweep.py --reference-point $SW --iterations 30 \
    --out gpurun_out/r2_halo_sweep_P$N.json > gpurun_out/r2_halo_sweep_P$N.log 2>&1; echo "sweep rc=$?"; grep '^{' gpurun_out/r2_halo_sweep_P$N.log | head -40
 echo "== reference self-checking halo scripts on $N GPUs"
 M=vertical; [ "$N" = "4" ] && M=square
-timeout 120 $TR --nproc-per-node $N --master-port 29702 benchmarks/communication/halo/benchmark_sp_halo_exchange_conv.py --image-size 1024 \
-   --halo-len 3 --num-spatial-parts $N --slice-method $M --in-channels 1 --out-channels 256 --iterations 100 \
+# (known answers are exact integers only while the 7x7 box sums stay below 2^24: validate at 128^2, time at 1024^2)
+timeout 120 $TR --nproc-per-node $N --master-port 29702 benchmarks/communication/halo/benchmark_sp_halo_exchange_conv.py --image-size 128 \
+   --halo-len 3 --num-spatial-parts $N --slice-method $M --in-channels 1 --out-channels 256 --iterations 20 \
    --enable-val-recv-tensors --enable-val-conv 2>&1 | grep "Rank:" | sort | head -20
+timeout 120 $TR --nproc-per-node $N --master-port 29706 benchmarks/communication/halo/benchmark_sp_halo_exchange_with_compute.py --image-size 1024 \
+   --halo-len 3 --num-spatial-parts $N --slice-method $M --iterations 100 2>&1 | grep "Rank:" | sort | head -20
 timeout 120 $TR --nproc-per-node $N --master-port 29703 benchmarks/communication/halo/benchmark_sp_halo_exchange.py --image-size 1024 \
    --halo-len 3 --num-spatial-parts $N --slice-method vertical 2>&1 | grep "Rank:" | sort | head -20
 echo "== bench N=$N"
-timeout 400 $TR --nproc-per-node $N --master-port 29704 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err
+timeout 300 $TR --nproc-per-node $N --master-port 29704 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err
 echo "bench rc=$?"; grep "bench " gpurun_out/r2_bench_n$N.err | tail -6
 python -c "
 import json;d=json.load(open('gpurun_out/r2_bench_n$N.json'));print('N=$N', d['ms_per_step'], d['value'], d['e2e']['value'], d['config']['launch_mode'], d['gpu_launches'])"
-timeout 300 $TR --nproc-per-node $N --master-port 29705 bench.py --gpus $N --steps 10 --warmup 3 --graph off > gpurun_out/r2_bench_n${N}_eager.json 2> gpurun_out/r2_bench_n${N}_eager.err
+timeout 200 $TR --nproc-per-node $N --master-port 29705 bench.py --gpus $N --steps 10 --warmup 3 --graph off > gpurun_out/r2_bench_n${N}_eager.json 2> gpurun_out/r2_bench_n${N}_eager.err
 python -c "
 import json;d=json.load(open('gpurun_out/r2_bench_n${N}_eager.json'));print('N=$N eager', d['ms_per_step'], d['value'], d['e2e']['value'])"
 if [ "$N" = "2" ]; then
