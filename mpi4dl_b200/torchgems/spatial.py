@@ -128,13 +128,14 @@ class _SpatialTopology:
         # (world = k * mp_size, mp_pipeline's replica base): the tile line starts at this replica's first rank.
         if dist.is_available() and dist.is_initialized() and self.local_rank != dist.get_rank():
             world_size, rank = dist.get_world_size(), dist.get_rank()
-            if world_size - 1 - rank == self.local_rank:
+            base = rank - self.local_rank
+            if world_size - 1 - rank == self.local_rank or base <= 0:
+                # (base <= 0: the scripts also BUILD the spatial cells on ranks that never run them, with
+                # local_rank = position % tiles -- keep the reference's formula there, the layers stay idle)
                 for i in range(9):
                     if self.neighbours[i] == 1:
                         self.rank_neighbours[i] = world_size - 1 - self.rank_neighbours[i]
             else:
-                base = rank - self.local_rank
-                assert base > 0, "conv_spatial: local_rank %d does not belong to world rank %d" % (self.local_rank, rank)
                 for i in range(9):
                     if self.neighbours[i] == 1:
                         self.rank_neighbours[i] += base
@@ -280,23 +281,34 @@ class conv_spatial(nn.Conv2d, _SpatialTopology):
         self.set_tags()
         self.algo = _lib.SPC_ALGO_AUTO
 
-    def _crop_fused(self, y, H, W):
+    def _fused_pre(self, x):
+        """D2 variant, strided: a side that faces a neighbour carries NO padding, so the sampling phase of a strided
+        convolution starts at the tile's first row / column, while the "same"-padded kernel starts `pad` before it.
+        When pad % stride != 0 the two grids never coincide; prepending (stride - pad % stride) dummy rows / columns
+        (zeros; no valid output window ever reads them) re-aligns them.  Returns (x', extra_top, extra_left)."""
+        sh, sw = self.stride
+        ph, pw = self.halo_len_height, self.halo_len_width
+        top, _, left, _ = self._inner_sides
+        et = (sh - ph % sh) % sh if (top and ph % sh) else 0
+        el = (sw - pw % sw) % sw if (left and pw % sw) else 0
+        if et or el:
+            x = torch.nn.functional.pad(x, (el, 0, et, 0))
+        return x, et, el
+
+    def _crop_fused(self, y, H, W, et=0, el=0):
         """Drop the output rows / columns whose window would reach past a neighbour-facing edge
-        (those sides carry no padding in the D2 variant)."""
+        (those sides carry no padding in the D2 variant).  H, W: the ORIGINAL tile extent; et / el: dummy rows /
+        columns prepended by _fused_pre."""
         R, S = self.kernel_size
         sh, sw = self.stride
         ph, pw = self.halo_len_height, self.halo_len_width
         Ho, Wo = y.shape[2], y.shape[3]
         top, bottom, left, right = self._inner_sides
-        if (top and ph % sh) or (left and pw % sw):
-            # an unpadded top/left edge shifts the sampling phase of a strided conv; that needs an
-            # asymmetric-pad kernel entry (next), cropping the "same" convolution is not equivalent
-            raise NotImplementedError("conv_spatial(halo_len=0) with stride > 1 on a tile whose top/left "
-                                      "side faces a neighbour is not supported yet")
-        y0 = -(-ph // sh) if top else 0                                   # first row with window start >= 0
-        y1 = min(Ho, (H - R + ph) // sh + 1) if bottom else Ho            # last row with window end < H
-        x0 = -(-pw // sw) if left else 0
-        x1 = min(Wo, (W - S + pw) // sw + 1) if right else Wo
+        # output index p of the padded run has its window start at s*p - pad - extra (in original coordinates)
+        y0 = (ph + et) // sh if top else 0                                  # first window starting at row 0
+        y1 = min(Ho, (H - R + ph + et) // sh + 1) if bottom else Ho         # last window ending inside the tile
+        x0 = (pw + el) // sw if left else 0
+        x1 = min(Wo, (W - S + pw + el) // sw + 1) if right else Wo
         return y[:, :, y0:y1, x0:x1]
 
     def forward(self, tensor):
@@ -305,6 +317,10 @@ class conv_spatial(nn.Conv2d, _SpatialTopology):
         if x.dtype != self.weight.dtype:
             raise RuntimeError("conv_spatial: input dtype %s != weight dtype %s" % (x.dtype, self.weight.dtype))
         hh, hw = self.halo_len_height, self.halo_len_width
+        H0, W0 = x.shape[2], x.shape[3]
+        et = el = 0
+        if self.fused_halo:
+            x, et, el = self._fused_pre(x)
         N, Cc, H, W = x.shape
         desc_args = (N, Cc, H, W, self.out_channels, self.kernel_size[0], self.kernel_size[1], self.stride[0],
                      self.stride[1], hh, hw, _lib.dtype_code(x.dtype), self.algo)
@@ -329,7 +345,7 @@ class conv_spatial(nn.Conv2d, _SpatialTopology):
                 strips = self._exchange(x, hh, hw) if exchange else [None] * 9
         y = _ConvSpatialFn.apply(x, self.weight, self.bias, desc_args, *strips, *extra)
         if self.fused_halo:
-            y = self._crop_fused(y, H, W)
+            y = self._crop_fused(y, H0, W0, et, el)
         return y
 
 
