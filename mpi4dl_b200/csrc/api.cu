@@ -6,6 +6,8 @@
 // received strips in place.  Interior compute therefore never waits on the halo exchange --
 // the overlap the reference left as dead code (spatial.py:415-866).  Everything else runs
 // entirely on the direct kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace spc {
@@ -105,6 +107,84 @@ static int patch_wgrad_rect(const spc_conv_desc* d, const spc_halo* halo, const 
   return tc_conv_wgrad(&q, P, G, dw, 1, ws, wsb, st);
 }
 
+// ---- halo fix-up of the tcgen05 paths: a small GEMM over the boundary outputs only ------------------------------
+// After the interior pass ran the whole tile with zero padding, the outputs whose window reaches a received strip
+// miss exactly   sum_{c,r,s : tap outside the tile} w[k][c][r][s] * halo(c, tap)   -- linear in the halo pixels.
+// V[(c,r,s)][p] (im2col of the HALO-ONLY view over the P_b boundary outputs) turns that into one pointwise GEMM
+// O[K][P_b] = w[K][C*R*S] * V  on the tcgen05 kernel (the filter tensor IS that matrix, no repack of taps) + a
+// scatter-add; and the halo's share of wgrad into  dW[K][C*R*S] += dY_b[K][P_b] * V^T  (pw_wgrad_kernel, accumulating
+// straight into dw).  Round 1 gathered a 64-column-aligned patch around every boundary rectangle and re-ran the
+// convolution on it (3 launches per rectangle, up to 4 rectangles; strided layers fell to the direct kernel on thin
+// strips): +0.18 ms per 1x7 fprop and +0.59 ms per wgrad on the 1024x128 tiles of an 8-GPU run
+// (profiles/r2_halo_cost_n8.txt), more than the interior pass itself.
+static bool boundary_rects(const spc_conv_desc* d, const spc_halo* halo, int Ho, int Wo, BoundaryRects* b) {
+  const int top = min(Ho, ceil_div(d->pad_h, d->stride_h));
+  int bot0 = ceil_div(d->H + d->pad_h - d->R + 1, d->stride_h);      // first output row touching the bottom halo
+  bot0 = max(top, min(Ho, bot0));
+  const int left = min(Wo, ceil_div(d->pad_w, d->stride_w));
+  int right0 = ceil_div(d->W + d->pad_w - d->S + 1, d->stride_w);
+  right0 = max(left, min(Wo, right0));
+  const bool any_top = halo->strip[0] || halo->strip[1] || halo->strip[2];
+  const bool any_bot = halo->strip[6] || halo->strip[7] || halo->strip[8];
+  const bool any_left = halo->strip[0] || halo->strip[3] || halo->strip[6];
+  const bool any_right = halo->strip[2] || halo->strip[5] || halo->strip[8];
+  const int sy0 = any_top ? top : 0, sy1 = any_bot ? bot0 : Ho;       // rows not already covered by the bands
+  int n = 0, acc = 0;
+  auto add = [&](int y0, int y1, int x0, int x1) {
+    if (y1 <= y0 || x1 <= x0) return;
+    b->y0[n] = y0; b->y1[n] = y1; b->x0[n] = x0; b->x1[n] = x1;
+    b->start[n] = acc;
+    acc += (y1 - y0) * (x1 - x0);
+    ++n;
+  };
+  if (any_top) add(0, top, 0, Wo);
+  if (any_bot) add(bot0, Ho, 0, Wo);
+  if (any_left) add(sy0, sy1, 0, left);
+  if (any_right) add(sy0, sy1, right0, Wo);
+  for (int i = n; i < 5; ++i) b->start[i] = acc;
+  for (int i = n; i < 4; ++i) { b->y0[i] = b->y1[i] = b->x0[i] = 0; b->x1[i] = 1; }
+  b->n = n; b->N = d->N; b->per_image = acc; b->total = acc * d->N;
+  b->padded = (b->total + 63) & ~63;
+  return b->total > 0;
+}
+
+static int boundary_fwd_tc(const spc_conv_desc* d, const spc_halo* halo, const void* w, void* y, cudaStream_t st) {
+  int Ho, Wo;
+  spc_conv_out_shape(d, &Ho, &Wo);
+  BoundaryRects b;
+  if (!boundary_rects(d, halo, Ho, Wo, &b)) return SPC_OK;
+  const int CT = d->C * d->R * d->S;
+  const size_t vbytes = al256((size_t)CT * b.padded * 2), obytes = al256((size_t)d->K * b.padded * 2);
+  const size_t wsb = tc_pw_workspace_bytes(d->K, CT);
+  char* base = (char*)boundary_scratch(vbytes + obytes + wsb + 2048);
+  SPC_REQUIRE(base != nullptr, "boundary scratch allocation failed");
+  void* V = base; void* O = base + vbytes; void* ws = base + vbytes + obytes;
+  TileView v = make_view(nullptr, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);   // halo pixels only
+  int rc = launch_halo_im2col(v, b, d->R, d->S, d->stride_h, d->stride_w, d->pad_h, d->pad_w, V, st);
+  if (rc) return rc;
+  rc = tc_pw_fwd(w, CT, d->K, CT, V, O, b.padded, ws, wsb, st);
+  if (rc) return rc;
+  return launch_boundary_scatter_add(O, b, d->K, Ho, Wo, y, st);
+}
+
+static int boundary_wgrad_tc(const spc_conv_desc* d, const spc_halo* halo, const void* dy, float* dw, cudaStream_t st) {
+  int Ho, Wo;
+  spc_conv_out_shape(d, &Ho, &Wo);
+  BoundaryRects b;
+  if (!boundary_rects(d, halo, Ho, Wo, &b)) return SPC_OK;
+  const int CT = d->C * d->R * d->S;
+  const size_t vbytes = al256((size_t)CT * b.padded * 2), gbytes = al256((size_t)d->K * b.padded * 2);
+  char* base = (char*)boundary_scratch(vbytes + gbytes + 2048);
+  SPC_REQUIRE(base != nullptr, "boundary scratch allocation failed");
+  void* V = base; void* G = base + vbytes;
+  TileView v = make_view(nullptr, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);
+  int rc = launch_halo_im2col(v, b, d->R, d->S, d->stride_h, d->stride_w, d->pad_h, d->pad_w, V, st);
+  if (rc) return rc;
+  rc = launch_boundary_gather(dy, b, d->K, Ho, Wo, G, st);
+  if (rc) return rc;
+  return tc_pw_wgrad(V, G, dw, d->K, CT, b.padded, st);   // dw[k][(c,r,s)] += sum_p G[k][p] * V[(c,r,s)][p]
+}
+
 // Launch the direct kernel on the output sub-rectangle [y0,y1) x [x0,x1).
 int fwd_rect(DirectConvParams p, int dtype, int y0, int y1, int x0, int x1, cudaStream_t st) {
   if (y1 <= y0 || x1 <= x0) return SPC_OK;
@@ -154,6 +234,8 @@ static int fwd_boundary(const spc_conv_desc* d, DirectConvParams p, const spc_ha
   const bool any_left = halo->strip[0] || halo->strip[3] || halo->strip[6];
   const bool any_right = halo->strip[2] || halo->strip[5] || halo->strip[8];
   const int sy0 = any_top ? top : 0, sy1 = any_bot ? bot0 : Ho;   // rows not already redone by the bands
+  if (d->dtype == SPC_BF16 && d->algo != SPC_ALGO_DIRECT && !getenv("SPC_BOUNDARY_V1"))
+    return boundary_fwd_tc(d, halo, p.w, p.y, st);
   if (patch_ok(d, 0)) {
     const void* x = p.in.x; const void* w = p.w; const void* bias = p.bias; void* y = p.y;
     if (any_top && (rc = patch_fwd_rect(d, x, halo, w, bias, y, 0, top, 0, Wo, st))) return rc;
@@ -295,7 +377,10 @@ int spc_conv2d_wgrad(const spc_conv_desc* d, const void* x, const spc_halo* halo
       // add the halo pixels' contribution: the direct kernel over a view that holds ONLY the
       // strips (interior reads as zero) -- exact by linearity -- restricted to the output strips
       // whose windows reach outside the tile.
-      if (patch_ok(d, 2)) {
+      if (d->dtype == SPC_BF16 && !getenv("SPC_BOUNDARY_V1")) {
+        rc = boundary_wgrad_tc(d, halo, dy, dw, st);
+        if (rc) return rc;
+      } else if (patch_ok(d, 2)) {
         const int top = min(Ho, d->pad_h), bot0 = max(top, min(Ho, d->H + d->pad_h - d->R + 1));
         const int left = min(Wo, d->pad_w), right0 = max(left, min(Wo, d->W + d->pad_w - d->S + 1));
         const bool any_top = halo->strip[0] || halo->strip[1] || halo->strip[2];

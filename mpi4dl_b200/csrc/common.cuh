@@ -140,6 +140,27 @@ int launch_patch_gather_dy(const void* dy, void* G, int NK, int Ho, int Wo, int 
 int launch_patch_scatter(const void* O, void* y, int NK, int Ho, int Wo, int Hp, int Wp, int y0, int x0, int rh, int rw,
                          int ph, int pw, int dtype, cudaStream_t st);
 
+// ---- halo fix-up as a small GEMM over the boundary outputs only (halo.cu kernels, api.cu orchestration) ----------
+// The boundary outputs of a tile (those whose window reaches a received strip) are listed as <= 4 disjoint output
+// rectangles; P_b = their pixel count (x N), padded to a multiple of 64.
+struct BoundaryRects {
+  int n;                       // rectangles in use
+  int y0[4], y1[4], x0[4], x1[4];
+  int start[5];                // prefix sums of the pixel counts PER IMAGE
+  int N, per_image, total;     // images, pixels per image, N * per_image
+  int padded;                  // total rounded up to 64
+};
+// V[(c,r,s)][p] = the HALO pixel the tap (r,s) of boundary output p reads in channel c (0 where the tap stays inside
+// the tile or no strip is there): the im2col of the halo-only view, bf16
+int launch_halo_im2col(const TileView& halo_only, const BoundaryRects& b, int R, int S, int sh, int sw, int ph, int pw, void* V,
+                       cudaStream_t st);
+// G[k][p] = dy[n][k][i][j] at the boundary outputs;  y[n][k][i][j] += O[k][p]
+int launch_boundary_gather(const void* dy, const BoundaryRects& b, int K, int Ho, int Wo, void* G, cudaStream_t st);
+int launch_boundary_scatter_add(const void* O, const BoundaryRects& b, int K, int Ho, int Wo, void* y, cudaStream_t st);
+size_t tc_pw_workspace_bytes(int M, int Cin);
+int tc_pw_fwd(const void* w, int ld, int M, int Cin, const void* x, void* y, int P, void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_pw_wgrad(const void* x, const void* dy, float* dw, int K, int C, int P, cudaStream_t st);
+
 // ---- tcgen05 pointwise GEMM path: gemm_tc.cu ---------------------------------------------
 bool tc_supported(const spc_conv_desc* d, int op);
 size_t tc_workspace_bytes(const spc_conv_desc* d, int op);

@@ -285,6 +285,66 @@ __global__ void halo_collect_kernel(const CollectParams p, const FlagSet f) {
   signal_when_grid_done(f, seq);
 }
 
+
+// ---- halo fix-up over the boundary outputs only ------------------------------------------------------------------
+__device__ __forceinline__ void boundary_decode(const BoundaryRects& b, int p, int& n, int& i, int& j) {
+  n = p / b.per_image;
+  const int q = p - n * b.per_image;
+  int r = 0;
+#pragma unroll
+  for (int t = 1; t < 4; ++t) r += (t < b.n && q >= b.start[t]) ? 1 : 0;
+  const int e = q - b.start[r];
+  const int rw = b.x1[r] - b.x0[r];
+  i = b.y0[r] + e / rw;
+  j = b.x0[r] + e % rw;
+}
+
+__global__ void halo_im2col_kernel(const TileView v, const BoundaryRects b, int R, int S, int sh, int sw, int ph, int pw,
+                                   __nv_bfloat16* __restrict__ V) {
+  const size_t total = (size_t)v.C * R * S * b.padded;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % b.padded);
+    const int ct = (int)(idx / b.padded);
+    float val = 0.f;
+    if (p < b.total) {
+      int n, i, j;
+      boundary_decode(b, p, n, i, j);
+      const int s = ct % S, r = (ct / S) % R, c = ct / (R * S);
+      val = tile_load<__nv_bfloat16>(v, n, c, i * sh + r - ph, j * sw + s - pw);   // halo-only view: 0 inside the tile
+    }
+    V[idx] = __float2bfloat16(val);
+  }
+}
+
+__global__ void boundary_gather_kernel(const __nv_bfloat16* __restrict__ dy, const BoundaryRects b, int K, int Ho, int Wo,
+                                       __nv_bfloat16* __restrict__ G) {
+  const size_t total = (size_t)K * b.padded;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % b.padded);
+    const int k = (int)(idx / b.padded);
+    __nv_bfloat16 val = __float2bfloat16(0.f);
+    if (p < b.total) {
+      int n, i, j;
+      boundary_decode(b, p, n, i, j);
+      val = dy[(((size_t)n * K + k) * Ho + i) * Wo + j];
+    }
+    G[idx] = val;
+  }
+}
+
+__global__ void boundary_scatter_add_kernel(const __nv_bfloat16* __restrict__ O, const BoundaryRects b, int K, int Ho, int Wo,
+                                            __nv_bfloat16* __restrict__ y) {
+  const size_t total = (size_t)K * b.total;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % b.total);
+    const int k = (int)(idx / b.total);
+    int n, i, j;
+    boundary_decode(b, p, n, i, j);
+    __nv_bfloat16* dst = y + (((size_t)n * K + k) * Ho + i) * Wo + j;
+    *dst = __float2bfloat16(__bfloat162float(*dst) + __bfloat162float(O[(size_t)k * b.padded + p]));
+  }
+}
+
 inline int grid_for(size_t total) {
   size_t b = (total + 255) / 256;
   if (b > 148 * 16) b = 148 * 16;
@@ -296,6 +356,31 @@ inline int grid_for(size_t total) {
 }  // namespace spc
 
 namespace spc {
+int launch_halo_im2col(const TileView& halo_only, const BoundaryRects& b, int R, int S, int sh, int sw, int ph, int pw, void* V,
+                       cudaStream_t st) {
+  const size_t total = (size_t)halo_only.C * R * S * b.padded;
+  if (!total) return SPC_OK;
+  halo_im2col_kernel<<<grid_for(total), 256, 0, st>>>(halo_only, b, R, S, sh, sw, ph, pw, (__nv_bfloat16*)V);
+  count_launch();
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+int launch_boundary_gather(const void* dy, const BoundaryRects& b, int K, int Ho, int Wo, void* G, cudaStream_t st) {
+  const size_t total = (size_t)K * b.padded;
+  if (!total) return SPC_OK;
+  boundary_gather_kernel<<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)dy, b, K, Ho, Wo, (__nv_bfloat16*)G);
+  count_launch();
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
+int launch_boundary_scatter_add(const void* O, const BoundaryRects& b, int K, int Ho, int Wo, void* y, cudaStream_t st) {
+  const size_t total = (size_t)K * b.total;
+  if (!total) return SPC_OK;
+  boundary_scatter_add_kernel<<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)O, b, K, Ho, Wo, (__nv_bfloat16*)y);
+  count_launch();
+  SPC_CHECK_CUDA(cudaGetLastError());
+  return SPC_OK;
+}
 int launch_patch_gather(const TileView& v, void* P, int Hp, int Wp, int h0, int w0, int dtype, cudaStream_t st) {
   const size_t total = (size_t)v.N * v.C * Hp * Wp;
   if (!total) return SPC_OK;
