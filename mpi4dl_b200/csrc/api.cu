@@ -108,15 +108,15 @@ static int patch_wgrad_rect(const spc_conv_desc* d, const spc_halo* halo, const 
 }
 
 // ---- halo fix-up of the tcgen05 paths: a small GEMM over the boundary outputs only ------------------------------
-// After the interior pass ran the whole tile with zero padding, the outputs whose window reaches a received strip
-// miss exactly   sum_{c,r,s : tap outside the tile} w[k][c][r][s] * halo(c, tap)   -- linear in the halo pixels.
-// V[(c,r,s)][p] (im2col of the HALO-ONLY view over the P_b boundary outputs) turns that into one pointwise GEMM
-// O[K][P_b] = w[K][C*R*S] * V  on the tcgen05 kernel (the filter tensor IS that matrix, no repack of taps) + a
-// scatter-add; and the halo's share of wgrad into  dW[K][C*R*S] += dY_b[K][P_b] * V^T  (pw_wgrad_kernel, accumulating
-// straight into dw).  Round 1 gathered a 64-column-aligned patch around every boundary rectangle and re-ran the
-// convolution on it (3 launches per rectangle, up to 4 rectangles; strided layers fell to the direct kernel on thin
-// strips): +0.18 ms per 1x7 fprop and +0.59 ms per wgrad on the 1024x128 tiles of an 8-GPU run
-// (profiles/r2_halo_cost_n8.txt), more than the interior pass itself.
+// After the interior pass ran the whole tile with zero padding, only the outputs whose window reaches a received
+// strip are wrong (P_b of them: a few rows / columns).  fprop: V[(c,r,s)][p] = im2col of tile + strips over those
+// P_b outputs, then ONE pointwise GEMM  O[K][P_b] = w[K][C*R*S] * V (+bias)  on the tcgen05 kernel -- the filter tensor
+// IS that matrix -- and a scatter that overwrites them.  wgrad: the halo pixels' share is linear, so with V taken
+// from the HALO-ONLY view  dW[K][C*R*S] += dY_b[K][P_b] * V^T  (pw_wgrad_kernel accumulating straight into dw).
+// Round 1 gathered a 64-column-aligned patch around every boundary rectangle and re-ran the convolution on it
+// (3 launches per rectangle, up to 4 rectangles; strided layers fell to the direct kernel on thin strips): +0.18 ms
+// per 1x7 fprop and +0.59 ms per wgrad on the 1024x128 tiles of an 8-GPU run (profiles/r2_halo_cost_n8.txt) -- more
+// than the interior pass itself; now +0.07 / +0.08 ms (profiles/r2_halo_cost_n8_v2.txt).
 static bool boundary_rects(const spc_conv_desc* d, const spc_halo* halo, int Ho, int Wo, BoundaryRects* b) {
   const int top = min(Ho, ceil_div(d->pad_h, d->stride_h));
   int bot0 = ceil_div(d->H + d->pad_h - d->R + 1, d->stride_h);      // first output row touching the bottom halo
@@ -148,7 +148,8 @@ static bool boundary_rects(const spc_conv_desc* d, const spc_halo* halo, int Ho,
   return b->total > 0;
 }
 
-static int boundary_fwd_tc(const spc_conv_desc* d, const spc_halo* halo, const void* w, void* y, cudaStream_t st) {
+static int boundary_fwd_tc(const spc_conv_desc* d, const void* x, const spc_halo* halo, const void* w, const void* bias,
+                           void* y, cudaStream_t st) {
   int Ho, Wo;
   spc_conv_out_shape(d, &Ho, &Wo);
   BoundaryRects b;
@@ -159,12 +160,15 @@ static int boundary_fwd_tc(const spc_conv_desc* d, const spc_halo* halo, const v
   char* base = (char*)boundary_scratch(vbytes + obytes + wsb + 2048);
   SPC_REQUIRE(base != nullptr, "boundary scratch allocation failed");
   void* V = base; void* O = base + vbytes; void* ws = base + vbytes + obytes;
-  TileView v = make_view(nullptr, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);   // halo pixels only
+  // fprop gathers the FULL windows (tile + strips) of the boundary outputs and overwrites them: the result is rounded
+  // to bf16 once, like every other output (adding a halo-only correction to the already rounded interior value
+  // rounds twice -- 335 of 4.4e8 stem outputs left the parity tolerance that way)
+  TileView v = make_view(x, halo, d->N, d->C, d->H, d->W, d->pad_h, d->pad_w);
   int rc = launch_halo_im2col(v, b, d->R, d->S, d->stride_h, d->stride_w, d->pad_h, d->pad_w, V, st);
   if (rc) return rc;
-  rc = tc_pw_fwd(w, CT, d->K, CT, V, O, b.padded, ws, wsb, st);
+  rc = tc_pw_fwd(w, CT, d->K, CT, V, bias, O, b.padded, ws, wsb, st);
   if (rc) return rc;
-  return launch_boundary_scatter_add(O, b, d->K, Ho, Wo, y, st);
+  return launch_boundary_scatter(O, b, d->K, Ho, Wo, y, st);
 }
 
 static int boundary_wgrad_tc(const spc_conv_desc* d, const spc_halo* halo, const void* dy, float* dw, cudaStream_t st) {
@@ -235,7 +239,7 @@ static int fwd_boundary(const spc_conv_desc* d, DirectConvParams p, const spc_ha
   const bool any_right = halo->strip[2] || halo->strip[5] || halo->strip[8];
   const int sy0 = any_top ? top : 0, sy1 = any_bot ? bot0 : Ho;   // rows not already redone by the bands
   if (d->dtype == SPC_BF16 && d->algo != SPC_ALGO_DIRECT && !getenv("SPC_BOUNDARY_V1"))
-    return boundary_fwd_tc(d, halo, p.w, p.y, st);
+    return boundary_fwd_tc(d, p.in.x, halo, p.w, p.bias, p.y, st);
   if (patch_ok(d, 0)) {
     const void* x = p.in.x; const void* w = p.w; const void* bias = p.bias; void* y = p.y;
     if (any_top && (rc = patch_fwd_rect(d, x, halo, w, bias, y, 0, top, 0, Wo, st))) return rc;

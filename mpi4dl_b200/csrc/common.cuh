@@ -150,15 +150,16 @@ struct BoundaryRects {
   int N, per_image, total;     // images, pixels per image, N * per_image
   int padded;                  // total rounded up to 64
 };
-// V[(c,r,s)][p] = the HALO pixel the tap (r,s) of boundary output p reads in channel c (0 where the tap stays inside
-// the tile or no strip is there): the im2col of the halo-only view, bf16
+// V[(c,r,s)][p] = the pixel the tap (r,s) of boundary output p reads in channel c, through `view`: tile + strips for
+// fprop (full windows), the halo-only view for wgrad (0 where the tap stays inside the tile); bf16
 int launch_halo_im2col(const TileView& halo_only, const BoundaryRects& b, int R, int S, int sh, int sw, int ph, int pw, void* V,
                        cudaStream_t st);
-// G[k][p] = dy[n][k][i][j] at the boundary outputs;  y[n][k][i][j] += O[k][p]
+// G[k][p] = dy[n][k][i][j] at the boundary outputs;  y[n][k][i][j] = O[k][p]
 int launch_boundary_gather(const void* dy, const BoundaryRects& b, int K, int Ho, int Wo, void* G, cudaStream_t st);
-int launch_boundary_scatter_add(const void* O, const BoundaryRects& b, int K, int Ho, int Wo, void* y, cudaStream_t st);
+int launch_boundary_scatter(const void* O, const BoundaryRects& b, int K, int Ho, int Wo, void* y, cudaStream_t st);
 size_t tc_pw_workspace_bytes(int M, int Cin);
-int tc_pw_fwd(const void* w, int ld, int M, int Cin, const void* x, void* y, int P, void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_pw_fwd(const void* w, int ld, int M, int Cin, const void* x, const void* bias, void* y, int P, void* ws, size_t ws_bytes,
+              cudaStream_t st);
 int tc_pw_wgrad(const void* x, const void* dy, float* dw, int K, int C, int P, cudaStream_t st);
 
 // ---- tcgen05 pointwise GEMM path: gemm_tc.cu ---------------------------------------------

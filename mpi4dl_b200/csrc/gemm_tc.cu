@@ -1391,9 +1391,10 @@ int tc_conv_wgrad(const spc_conv_desc* d, const void* x, const void* dy, float* 
 // the pointwise tcgen05 kernels -- used by the halo fix-up (api.cu), where "channels" are (c, r, s) triples of the
 // filter and "pixels" are the boundary outputs
 size_t tc_pw_workspace_bytes(int M, int Cin) { return (size_t)round_up(M, 128) * round_up(Cin, BK) * 2 + 4096; }
-int tc_pw_fwd(const void* w, int ld, int M, int Cin, const void* x, void* y, int P, void* ws, size_t ws_bytes, cudaStream_t st) {
-  return run_pw(reinterpret_cast<const __nv_bfloat16*>(w), ld, 0, M, Cin, reinterpret_cast<const __nv_bfloat16*>(x), nullptr,
-                reinterpret_cast<__nv_bfloat16*>(y), 1, P, ws, ws_bytes, st);
+int tc_pw_fwd(const void* w, int ld, int M, int Cin, const void* x, const void* bias, void* y, int P, void* ws, size_t ws_bytes,
+              cudaStream_t st) {
+  return run_pw(reinterpret_cast<const __nv_bfloat16*>(w), ld, 0, M, Cin, reinterpret_cast<const __nv_bfloat16*>(x),
+                reinterpret_cast<const __nv_bfloat16*>(bias), reinterpret_cast<__nv_bfloat16*>(y), 1, P, ws, ws_bytes, st);
 }
 int tc_pw_wgrad(const void* x, const void* dy, float* dw, int K, int C, int P, cudaStream_t st) {
   return run_wgrad(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), dw, K, C, 1, 1, P, 1, 1, 1,

@@ -332,7 +332,7 @@ __global__ void boundary_gather_kernel(const __nv_bfloat16* __restrict__ dy, con
   }
 }
 
-__global__ void boundary_scatter_add_kernel(const __nv_bfloat16* __restrict__ O, const BoundaryRects b, int K, int Ho, int Wo,
+__global__ void boundary_scatter_kernel(const __nv_bfloat16* __restrict__ O, const BoundaryRects b, int K, int Ho, int Wo,
                                             __nv_bfloat16* __restrict__ y) {
   const size_t total = (size_t)K * b.total;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -340,8 +340,7 @@ __global__ void boundary_scatter_add_kernel(const __nv_bfloat16* __restrict__ O,
     const int k = (int)(idx / b.total);
     int n, i, j;
     boundary_decode(b, p, n, i, j);
-    __nv_bfloat16* dst = y + (((size_t)n * K + k) * Ho + i) * Wo + j;
-    *dst = __float2bfloat16(__bfloat162float(*dst) + __bfloat162float(O[(size_t)k * b.padded + p]));
+    y[(((size_t)n * K + k) * Ho + i) * Wo + j] = O[(size_t)k * b.padded + p];
   }
 }
 
@@ -373,10 +372,10 @@ int launch_boundary_gather(const void* dy, const BoundaryRects& b, int K, int Ho
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
 }
-int launch_boundary_scatter_add(const void* O, const BoundaryRects& b, int K, int Ho, int Wo, void* y, cudaStream_t st) {
+int launch_boundary_scatter(const void* O, const BoundaryRects& b, int K, int Ho, int Wo, void* y, cudaStream_t st) {
   const size_t total = (size_t)K * b.total;
   if (!total) return SPC_OK;
-  boundary_scatter_add_kernel<<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)O, b, K, Ho, Wo, (__nv_bfloat16*)y);
+  boundary_scatter_kernel<<<grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)O, b, K, Ho, Wo, (__nv_bfloat16*)y);
   count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;

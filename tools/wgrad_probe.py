@@ -32,6 +32,12 @@ PAIR_CONFIGS = [{}, dict(SPC_WG_2CTA="1"), dict(SPC_WG_2CTA="1", SPC_WG_STAGES="
 def main():
     quick = "--quick" in sys.argv
     global CONFIGS
+    global SHAPES
+    if "--splits" in sys.argv:
+        # flush cost: every work item adds its K x C accumulators to dw with fp32 atomics; sweep the item count
+        CONFIGS = [{}] + [dict(SPC_WG_SPLITS=str(v)) for v in (148, 74, 37, 18, 296)]
+        SHAPES = [(416, 416, 1024), (1664, 416, 1024), (104, 416, 1024), (104, 416, 360), (416, 416, 360), (416, 104, 360),
+                  (104, 208, 4096), (1248, 416, 360)]
     if "--pair" in sys.argv:
         # first run of the cta_group::2 kernel (never executed on hardware in round 1): ALWAYS under an outer
         # `timeout 90`, results are compared with the single-CTA kernel's dw (MISMATCH flag)
