@@ -702,18 +702,26 @@ int launch_wg(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMap& 
   SPC_REQUIRE(p.stages >= 2, "tcgen05 wgrad: smem budget");
   const int sms = sm_count();
   const int groups = p.mgroups * p.n_blocks * p.passes;
-  // items = groups * splits run on a persistent grid of `sms` CTAs: pick the split count whose item
-  // count fills whole waves (2 waves when possible).  Rounding UP here left a third, nearly empty
-  // wave for e.g. 14 groups x 22 splits = 308 items on 148 SMs (69 % efficiency).
+  // items = groups * splits on a persistent grid of `sms` CTAs.  Every item ends by adding its accumulators to dw with
+  // fp32 atomics, and that flush is a CHIP-WIDE cost (~90 G atomics/s measured, profiles/r2_wgrad_splits.txt): with
+  // few pixels per item it dominates (104->416 on a 1024x128 tile: 0.159 ms at 296 items, 0.082 at 74).  Pick the
+  // split count that minimises   waves * chunks_per_item * t_chunk + items * elems_per_item / 90e9,
+  // t_chunk = the slower of the item's MMA chain and its operand bytes at the per-SM share of L2 bandwidth.
   int splits = 1;
   {
-    double best = 0.0;
+    const double clk = 1.8e9;
+    const double bytes_chunk = (double)(MG * p.mrows + p.TG * p.nblk) * 128.0;
+    const double mma_chunk = (double)MG * p.TG * 4.0 * (p.nblk > 64 ? p.nblk : 64) / 256.0 * 222.0;
+    const double t_chunk = (bytes_chunk / 40.0 > mma_chunk ? bytes_chunk / 40.0 : mma_chunk) / clk;
+    const double elems = (double)MG * p.mrows * p.nblk * p.TG;
     const int smax = (2 * sms) / groups > 1 ? (2 * sms) / groups : 1;
-    for (int s = 1; s <= smax; ++s) {          // at most two waves; efficiency = items / (waves * sms)
+    double best = 1e30;
+    for (int s = smax; s >= 1; --s) {        // descending: near-ties keep the finer split (better balance)
+      if (s > p.chunks_total / 8 && s > 1) continue;
       const int items_s = groups * s, waves = (items_s + sms - 1) / sms;
-      const double eff = (double)items_s / ((double)waves * sms);
-      if (eff > best + 1e-9) { best = eff; splits = s; }
-      else if (eff > best - 0.02 && waves == 2) { splits = s; if (eff > best) best = eff; }   // prefer two waves
+      const double cpi = (double)((p.chunks_total + s - 1) / s);
+      const double t = waves * cpi * t_chunk + (double)items_s * elems / 90e9;
+      if (t < best * 0.98) { best = t; splits = s; }
     }
   }
   if (env_get("SPC_WG_SPLIT_CEIL")) splits = (2 * sms + groups - 1) / groups;   // previous behaviour (A/B knob)
@@ -888,14 +896,20 @@ int launch_wg_pair(const CUtensorMap& tdy, const CUtensorMap& tx, WgParams p, cu
   const int clusters = sms / 2;
   const int groups = p.mgroups * p.n_blocks;
   int splits = 1;
-  {
-    double best = 0.0;
+  {   // same cost model as launch_wg, per CTA pair
+    const double clk = 1.8e9;
+    const double bytes_chunk = (double)(MP * p.mrows + p.nblk / 2) * 128.0;          // per CTA
+    const double mma_chunk = (double)MP * 4.0 * (p.nblk > 64 ? p.nblk : 64) / 256.0 * 222.0;
+    const double t_chunk = (bytes_chunk / 40.0 > mma_chunk ? bytes_chunk / 40.0 : mma_chunk) / clk;
+    const double elems = 2.0 * MP * p.mrows * p.nblk;
     const int smax = (2 * clusters) / groups > 1 ? (2 * clusters) / groups : 1;
-    for (int s = 1; s <= smax; ++s) {
+    double best = 1e30;
+    for (int s = smax; s >= 1; --s) {
+      if (s > p.chunks_total / 8 && s > 1) continue;
       const int items_s = groups * s, waves = (items_s + clusters - 1) / clusters;
-      const double eff = (double)items_s / ((double)waves * clusters);
-      if (eff > best + 1e-9) { best = eff; splits = s; }
-      else if (eff > best - 0.02 && waves == 2) { splits = s; if (eff > best) best = eff; }
+      const double cpi = (double)((p.chunks_total + s - 1) / s);
+      const double t = waves * cpi * t_chunk + (double)items_s * elems / 90e9;
+      if (t < best * 0.98) { best = t; splits = s; }
     }
   }
   splits = env_int("SPC_WG_SPLITS", splits);
