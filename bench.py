@@ -618,9 +618,23 @@ def main():
             if not u["first"]:
                 fns.append(("dgrad", lambda: _lib.check(L.spc_conv2d_dgrad(C.byref(dsc), vp(gy), vp(w), vp(dx), vp(ws), nb, sp()), "dgrad"), bf["dgrad"], tc[1]))
             fns.append(("wgrad", lambda: _lib.check(L.spc_conv2d_wgrad(C.byref(dsc), vp(x), None, vp(gy), vp(dw), None, 0, vp(ws), nb, sp()), "wgrad"), bf["wgrad"], tc[2]))
+            def kernel_name(nm, is_tc):
+                """which libspconv kernel serves this (layer, op) -- the dispatch rules of csrc/gemm_tc.cu"""
+                if not is_tc:
+                    return "wgrad_direct_kernel" if nm == "wgrad" else "conv_direct_kernel"
+                taps, s1 = l["R"] * l["S"] > 1, l["stride_h"] == 1
+                if taps and s1 and u["tw"] % 64 == 0:
+                    if nm == "wgrad":
+                        if l["S"] > 1 and l["K"] <= 128 and l["C"] <= 128:
+                            return "wgrad_tap_kernel"
+                    elif (l["K"] if nm == "fprop" else l["C"]) <= 128:
+                        return "conv_tap_kernel"
+                if nm == "wgrad":
+                    return "pw_wgrad_pair_kernel" if (not taps and l["C"] >= 400 and l["K"] > 128) else "pw_wgrad_kernel"
+                return "pw_gemm_kernel"
+
             for nm, fn, (by, fl), is_tc in fns:
-                kern = ("pw_wgrad_kernel" if nm == "wgrad" else "pw_gemm_kernel") if is_tc else \
-                       ("wgrad_direct_kernel" if nm == "wgrad" else "conv_direct_kernel")
+                kern = kernel_name(nm, is_tc)
                 recs.append((nm, kern, ev_time(fn), by, fl))
             shape = "%d->%d %dx%d s%d @%dx%d" % (l["C"], l["K"], l["R"], l["S"], l["stride_h"], u["th"], u["tw"])
         else:
