@@ -36,6 +36,12 @@ def _builders(kind, args, mb, image_size, spatial_kw):
         from mpi4dl_b200.models import resnet, resnet_spatial
         seq_size, depth = 32, get_depth(2, 12)
         seq = resnet.get_resnet_v2((mb, 3, seq_size, seq_size), depth=depth, num_classes=args.num_classes)
+        if args.halo_d2:      # fused-halo cells (benchmark_resnet_sp.py:183-195): the builder also returns the balance it adjusted
+            from mpi4dl_b200.models import resnet_spatial_d2
+            model, new_balance = resnet_spatial_d2.get_resnet_v2(depth=depth, num_classes=args.num_classes,
+                                                                 fused_layers=args.fused_layers, **spatial_kw)
+            spatial_kw["balance_out"] = new_balance
+            return seq, seq_size, model
         model = resnet_spatial.get_resnet_v2(depth=depth, num_classes=args.num_classes, fused_layers=args.fused_layers,
                                              **spatial_kw)
         return seq, seq_size, model
@@ -91,8 +97,6 @@ def main(kind):
     num_spatial_parts = nsp[0] if len(nsp) == 1 else nsp
     P = nsp[0]
     balance = [int(v) for v in args.balance.split(",")] if args.balance else None
-    if args.halo_d2 and kind == "resnet":
-        raise NotImplementedError("--halo-D2 is built for AmoebaNet (models/amoebanet_d2.py); the ResNet D2 builder is not")
     if args.local_DP != 1:
         raise NotImplementedError("--local-DP > 1 is not built yet")
     verify_spatial_config(slice_method, image_size, nsp)
@@ -113,8 +117,9 @@ def main(kind):
     shapes = get_shapes_spatial(gen_seq.shape_list, slice_method, spatial_size, nsp, int(image_size / seq_size))
     del seq, gen_seq
 
+    # (the D2 ResNet builder inserts halo layers into stage 0 and hands back the balance that accounts for them)
     model_gen = model_generator(model=model.to(dtype), split_size=split_size, input_size=(mb, 3, image_size, image_size),
-                                balance=balance, shape_list=shapes)
+                                balance=spatial_kw.get("balance_out", balance), shape_list=shapes)
     model_gen.ready_model(split_rank=split_rank)
     del model
     trainer = train_model_spatial(model_gen, local_rank, batch_size, epochs=1, spatial_size=spatial_size,

@@ -254,8 +254,13 @@ class conv_spatial(nn.Conv2d, _SpatialTopology):
             # output shrinks there.  The reference hard-codes the 2x2 grid (ranks 0-3); here the
             # border sides follow from the rank grid, which is the same table for square-4.
             assert halo_len == 0, "Error: Custom Halo Len is not supported (only halo_len=0 is supported)"
-            assert (kernel_size[0] - 1) // 2 == padding[0] and (kernel_size[1] - 1) // 2 == padding[1], \
-                "conv_spatial(halo_len=0): padding must be (k-1)//2"
+            # padding = (k-1)//2: zero padding on the image-border sides only (amoebanet_d2.py);
+            # padding = 0: no padding on any side -- a valid convolution (resnet_spatial_d2.py:135-139 passes 0, and the
+            # reference's table puts `padding` on the border sides, spatial.py:75-104)
+            self._fused_valid = tuple(padding) == (0, 0)
+            assert self._fused_valid or ((kernel_size[0] - 1) // 2 == padding[0] and (kernel_size[1] - 1) // 2 == padding[1]), \
+                "conv_spatial(halo_len=0): padding must be (k-1)//2 or 0"
+            padding = ((kernel_size[0] - 1) // 2, (kernel_size[1] - 1) // 2)
         # spatial.py:115-121
         self.halo_len_height = int((kernel_size[0] - 1) / 2)
         self.halo_len_width = int((kernel_size[1] - 1) / 2)
@@ -275,7 +280,7 @@ class conv_spatial(nn.Conv2d, _SpatialTopology):
         if self.fused_halo:
             nb = self.neighbours or [0] * 9
             # sides with a neighbour: (top, bottom, left, right)
-            self._inner_sides = (bool(nb[1]), bool(nb[7]), bool(nb[3]), bool(nb[5]))
+            self._inner_sides = (True,) * 4 if self._fused_valid else (bool(nb[1]), bool(nb[7]), bool(nb[3]), bool(nb[5]))
             self.halo_len_height_d2, self.halo_len_width_d2 = 0, 0
             self.neighbours = None          # never exchanges
         self.set_tags()

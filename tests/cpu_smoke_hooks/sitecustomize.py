@@ -11,6 +11,8 @@ if os.environ.get("SPCONV_TEST_CPU_SMOKE") == "1":
     from mpi4dl_b200.torchgems import spatial
 
     def _conv(self, t):
+        if getattr(self, "_fused_valid", False):          # D2 ResNet cells: valid convolutions of the widened tile
+            return F.conv2d(t, self.weight, self.bias, self.stride, 0)
         return F.conv2d(t, self.weight, self.bias, self.stride, (self.halo_len_height, self.halo_len_width))
 
     def _pool(self, t):

@@ -28,6 +28,9 @@ SPATIAL_RUNS = [
     ("sp_amoebanet_d2_4tiles", 5, "spatial_parallelism/benchmark_amoebanet_sp.py",
      "--image-size 64 --num-spatial-parts 4 --slice-method square --split-size 2 --batch-size 1 --num-layers 6 "
      "--num-filters 64 --steps 2 --halo-D2"),
+    ("sp_resnet_d2_2tiles", 3, "spatial_parallelism/benchmark_resnet_sp.py",
+     "--image-size 64 --num-spatial-parts 2 --slice-method vertical --split-size 2 --batch-size 1 --steps 2 --halo-D2 "
+     "--fused-layers 2"),
     ("gems_sp_resnet", 4, "gems_master_with_spatial_parallelism/benchmark_resnet_gems_master_with_sp.py",
      "--split-size 3 --num-spatial-parts 2 --slice-method vertical --image-size 64 --batch-size 2 --times 2 --steps 2"),
     ("gems_sp_resnet_commopt", 4, "gems_master_with_spatial_parallelism/benchmark_resnet_gems_master_with_sp.py",

@@ -101,3 +101,40 @@ def test_cell_d2_matches_the_pytorch_operators_the_reference_calls():
         assert torch.allclose(a, b, rtol=2e-3, atol=2e-4)
     for a, b in zip(ours[3], ref[3]):
         assert torch.allclose(a, b, rtol=2e-3, atol=2e-4 * max(1.0, b.abs().max().item()))
+
+
+@pytest.mark.parametrize("strides,resblock", [(1, 1), (2, 0), (1, 0)])
+def test_resnet_d2_cell_is_valid_convolutions_with_cropped_shortcut(strides, resblock):
+    """make_cell_v2_spatial (models/resnet_spatial_d2.py; reference resnet_spatial_d2.py:396-480): every convolution is
+    conv_spatial(halo_len=0, padding=0) = a valid convolution on libspconv -- incl. the strided 3x3 and 1x1 ones, whose
+    sampling phase starts at the tile's first row / column -- and the shortcut is cropped by 2 (3 for stride 2).
+    Replayed with nn.Conv2d.forward on the same weights (the base class holds padding=0)."""
+    from mpi4dl_b200.models.resnet import _SpatialCtx  # noqa: F401
+    from mpi4dl_b200.models.resnet_spatial_d2 import _ValidCtx, make_cell_v2_spatial
+    from mpi4dl_b200.torchgems import spatial
+    torch.manual_seed(6)
+    ctx = _ValidCtx(0, 1, 4, "square")
+    cin = 64 if resblock else 16
+    cell = make_cell_v2_spatial(resblock, strides, cin, 16, 64, "relu", True, 2, ctx).cuda().train()
+    x = torch.randn(2, cin, 39, 71, device="cuda", requires_grad=True)     # odd extents: the strided phase matters
+
+    def run():
+        for p in cell.parameters():
+            p.grad = None
+        x.grad = None
+        y = cell(x)
+        y.square().mean().backward()
+        return y.detach().clone(), x.grad.clone(), [p.grad.clone() for p in cell.parameters() if p.grad is not None]
+
+    ours = run()
+    saved = spatial.conv_spatial.forward
+    try:
+        spatial.conv_spatial.forward = lambda self, t: nn.Conv2d.forward(self, t)
+        ref = run()
+    finally:
+        spatial.conv_spatial.forward = saved
+    assert ours[0].shape == ref[0].shape
+    for a, b in zip(ours[:2], ref[:2]):
+        assert torch.allclose(a, b, rtol=2e-3, atol=2e-4 * max(1.0, b.abs().max().item()))
+    for a, b in zip(ours[2], ref[2]):
+        assert torch.allclose(a, b, rtol=2e-3, atol=2e-4 * max(1.0, b.abs().max().item()))

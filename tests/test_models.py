@@ -136,3 +136,25 @@ def test_no_cudnn_conv_left_in_a_spatial_stage():
                 else:
                     assert type(x) is nn.Conv2d, (name, type(x))
     assert n_local == 13      # the 13 convolutions the reference leaves on cuDNN in these cells
+
+
+D2GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "model_d2_golden.json")))["resnet_d2"]
+
+
+@pytest.mark.parametrize("e", D2GOLD, ids=lambda e: "d%d_f%d_mp%d_%s" % (e["depth"], e["fused_layers"], e["kw"]["mp_size"],
+                                                                       "bal" if e["kw"]["balance"] else "even"))
+def test_resnet_d2_spatial_structure(e):
+    """D2 (fused halo) ResNet builder: the reference's keys, module order, halo widths (resnet_spatial_d2.py:651-698)
+    and the balance it returns."""
+    from mpi4dl_b200.models import resnet_spatial_d2
+    m, bal = resnet_spatial_d2.get_resnet_v2((2, 3, 64, 64), e["depth"], local_rank=0, spatial_size=1, num_spatial_parts=4,
+                                             slice_method="square", fused_layers=e["fused_layers"],
+                                             balance=list(e["kw"]["balance"]) if e["kw"]["balance"] else None,
+                                             mp_size=e["kw"]["mp_size"])
+    assert [n for n, _ in m.named_children()] == e["children"]
+    assert [[n, x.halo_len] for n, x in m.named_children() if type(x).__name__ == "halo_exchange_layer"] == [list(h) for h in e["halos"]]
+    assert list(bal) == e["balance"]
+    assert _sig(m) == e["state_sig"]
+    assert sum(p.numel() for p in m.parameters()) == e["params"]
+    kh, nconv, _ = _kinds(m)
+    assert (kh, nconv) == (e["kinds_sig"], e["spatial_convs"])
