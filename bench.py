@@ -216,7 +216,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def cudnn_baseline(torch, layers_unique, order, dev, steps, warmup):
+def cudnn_baseline(torch, layers_unique, order, dev, steps, warmup, full_size_cudnn=False):
     """The competitor BASELINE.md section 4 names: the identical layer list on STOCK PyTorch ops on the
     same B200 -- F.pad (the reference's ZeroPad2d copy, spatial.py:1020 / :1099, on every conv_spatial and
     every k>=3 Pool) + F.conv2d / F.*_pool2d (cuDNN / ATen) + autograd backward -- NCHW like the reference,
@@ -244,21 +244,22 @@ def cudnn_baseline(torch, layers_unique, order, dev, steps, warmup):
                 if l["op"] == "conv":
                     ws[key] = (torch.randn(l["K"], l["C"], l["R"], l["S"], dtype=dt, device=dev) * 0.05).requires_grad_(True)
 
-            def run_layer(key):
+            def run_layer(key, split=1):
                 u = layers_unique[key]
                 l = u["layer"]
-                n = u["in_shape"][1] * u["in_shape"][2] * u["in_shape"][3]
-                x = sx[:n].view(u["in_shape"]).detach()
+                ish = list(u["in_shape"])
+                ish[2] //= split                      # `split` > 1: the top 1/split of the tile (see `splits` below)
+                n = ish[1] * ish[2] * ish[3]
+                x = sx[:n].view(ish).detach()
                 if not u["first"]:
                     x.requires_grad_(True)
-                m = u["out_shape"][1] * u["out_shape"][2] * u["out_shape"][3]
-                gy = sg[:m].view(u["out_shape"])
                 if l["op"] == "conv":
                     xp = F.pad(x, (l["pad_w"], l["pad_w"], l["pad_h"], l["pad_h"])) if l.get("kind") == "conv_spatial" else x
                     y = F.conv2d(xp, ws[key], None, (l["stride_h"], l["stride_w"]), 0)
                 else:
                     xp = F.pad(x, (l["pad"],) * 4) if l["k"] >= 3 else x
                     y = (F.max_pool2d if l["mode"] == "max" else F.avg_pool2d)(xp, l["k"], l["stride"], 0)
+                gy = sg[:y.numel()].view(y.shape)
                 if y.requires_grad:
                     y.backward(gy)
                 x.grad = None
@@ -275,8 +276,12 @@ def cudnn_baseline(torch, layers_unique, order, dev, steps, warmup):
                 torch.cuda.synchronize()
                 return e0.elapsed_time(e1) / reps
 
-            # per layer: one warm-up call, then 1..3 timed calls (cuDNN's default heuristics pick pathologically slow
-            # kernels for a few of these shapes -- seconds per call -- so the repetition count adapts)
+            # per layer: one warm-up call, then 3 timed calls.  A convolution with a tensor of more than 2^31-1
+            # elements makes cuDNN's default heuristics fall back to kernels that take SECONDS per call (measured
+            # full-size on this B200: 3.9 s, 2.1 s, 11.3 s, 3.7 s for the four such layers, profiles/
+            # r2a_bench_n1_with_cudnn.json -- a 29.4 s step, and minutes of bench time).  Those layers are timed
+            # here on 1/split of the tile's rows and multiplied by split: cuDNN at its best, the comparison that
+            # is hardest on libspconv.
             per, step_ms = [], 0.0
             for key, u in layers_unique.items():
                 l = u["layer"]
@@ -284,10 +289,19 @@ def cudnn_baseline(torch, layers_unique, order, dev, steps, warmup):
                     shape = "%d->%d %dx%d s%d @%dx%d" % (l["C"], l["K"], l["R"], l["S"], l["stride_h"], u["th"], u["tw"])
                 else:
                     shape = "%s%d s%d C=%d @%dx%d" % (l["mode"], l["k"], l["stride"], l["C"], u["th"], u["tw"])
-                run_layer(key)
-                t1 = ev(lambda k=key: run_layer(k), 1)
-                ms = t1 if t1 > 50.0 else ev(lambda k=key: run_layer(k), 3)
-                per.append(dict(shape=shape, count=u["count"], fwd_bwd_ms=round(ms, 4)))
+                big = max(u["in_shape"][1] * u["in_shape"][2] * u["in_shape"][3],
+                          u["out_shape"][1] * u["out_shape"][2] * u["out_shape"][3])
+                split = 1
+                if l["op"] == "conv" and not full_size_cudnn:
+                    while big // split > 2**31 - 1:
+                        split *= 2
+                run_layer(key, split)
+                t1 = ev(lambda k=key, s_=split: run_layer(k, s_), 1)
+                ms = (t1 if t1 > 50.0 else ev(lambda k=key, s_=split: run_layer(k, s_), 3)) * split
+                e = dict(shape=shape, count=u["count"], fwd_bwd_ms=round(ms, 4))
+                if split > 1:
+                    e["timed_as"] = "%d x (1/%d of the rows)" % (split, split)
+                per.append(e)
                 step_ms += ms * u["count"]
             out[arm] = dict(ms_per_step=step_ms, images_per_sec=1000.0 / step_ms, per_layer=per)
             del sx, sg, ws
@@ -296,7 +310,10 @@ def cudnn_baseline(torch, layers_unique, order, dev, steps, warmup):
         torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     out["what"] = ("stock F.pad + F.conv2d / F.*_pool2d + autograd (cuDNN/ATen, NCHW, default heuristics) over the same "
                    "layer list and tile, CUDA events; fwd_bwd_ms = pad + fprop + dgrad + wgrad of one layer; "
-                   "ms_per_step = sum over the layer list of count * fwd_bwd_ms")
+                   "ms_per_step = sum over the layer list of count * fwd_bwd_ms; convolutions holding a tensor of more than 2^31-1 "
+                   "elements are timed on 1/split of the rows x split (entries with `timed_as`) because cuDNN takes "
+                   "seconds per call on them at full size (29.4 s/step, profiles/r2a_bench_n1_with_cudnn.json; "
+                   "--cudnn-full-size re-measures that)")
     return out
 
 
@@ -374,6 +391,8 @@ def main():
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the step from a CUDA graph (auto: when capture succeeds)")
     ap.add_argument("--no-cudnn-baseline", action="store_true")
+    ap.add_argument("--cudnn-full-size", action="store_true",
+                    help="time cuDNN on the whole tile even where a tensor exceeds 2^31-1 elements (adds minutes)")
     ap.add_argument("--no-model-stage", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -718,7 +737,7 @@ def main():
         cudnn = None
         if world == 1 and not args.no_cudnn_baseline:
             try:
-                cudnn = cudnn_baseline(torch, uniq, order, dev, min(args.steps, 5), 2)
+                cudnn = cudnn_baseline(torch, uniq, order, dev, min(args.steps, 5), 2, args.cudnn_full_size)
                 # where libspconv loses to stock cuDNN: our fprop+dgrad+wgrad (+ pool fwd+bwd) per layer vs its fwd_bwd
                 ours = {}
                 for o in ops:
