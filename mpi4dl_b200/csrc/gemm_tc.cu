@@ -139,6 +139,14 @@ struct PwParams {
   int rowmul;                  // input row = rowmul * output row + tap row offset (2 for stride-2 convs)
   int tgroup;                  // consecutive tiles handled back-to-back by one CTA (DRAM page locality)
   const __nv_bfloat16* bias;   // [M] or null
+  __nv_bfloat16* y;            // output base [N][M][P] (coalesced-store epilogue)
+  int epi_stg;                 // 1: staged tile leaves with per-thread 16-B stores (full 128-B lines), 0: TMA store
+  int x5, y5;                  // 1: activations / outputs move as ONE 5-d box per tile whose traversal order is
+                               // (8-channel group, 64-pixel block, channel, pixel): the TMA unit touches 8 channel
+                               // planes (2 MB pages each) at a time and visits both pixel blocks of each before moving
+                               // on, instead of walking 64 / 128 planes per pixel block (address-translation reach)
+  int xbox, ybox;              // channel rows per TMA load / store box (64 / 128 = one box per 64-pixel block; smaller
+                               // boxes walk FEWER channel planes -- 2 MB pages -- between the two pixel blocks of a tile)
 };
 
 template <int MB>
@@ -214,8 +222,17 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             st += MB * A_BLK_BYTES;
           }
           if (p.taps == 1) {
+            if (p.x5) {
+              tma_load_5d(st, &tmap_x, &full[s], 0, 0, p0 >> 6, kc * (BK / 8), n);
+            } else if (p.xbox == BK) {
 #pragma unroll
-            for (int j = 0; j < NB; ++j) tma_load_3d(st + j * B_BLK_BYTES, &tmap_x, &full[s], p0 + j * 64, kc * BK, n);
+              for (int j = 0; j < NB; ++j) tma_load_3d(st + j * B_BLK_BYTES, &tmap_x, &full[s], p0 + j * 64, kc * BK, n);
+            } else {
+              for (int cg = 0; cg < BK; cg += p.xbox)
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                  tma_load_3d(st + j * B_BLK_BYTES + cg * 128, &tmap_x, &full[s], p0 + j * 64, kc * BK + cg, n);
+            }
           } else {
             // shifted window of this tap; out-of-image rows / columns are zero-filled by TMA (= zero padding)
             const int dr = tap / p.S - p.ph;
@@ -252,7 +269,9 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           const int nsteps = min(4, ksteps_total - kc * 4);
           for (int ks = 0; ks < nsteps; ++ks) {
             // B: MN-major SW128. 16 channels = two 8-row groups (SBO = 1024 B); 64-px blocks at LBO = 8 KB
-            const uint64_t bdesc = umma_desc(sb + ks * 2048, B_BLK_BYTES, 1024);
+            // (5-d box layout [8-ch group][px block][8 ch][128 B]: px blocks at LBO = 1 KB, channel groups at SBO = 2 KB)
+            const uint64_t bdesc = p.x5 ? umma_desc(sb + ks * (NB * 2048), 1024, NB * 1024)
+                                        : umma_desc(sb + ks * 2048, B_BLK_BYTES, 1024);
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
               // A: K-major SW128. 8-row groups at SBO = 1024 B; +32 B per 16-channel k-step
@@ -290,15 +309,22 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const int k = k0 + row;
         const float bias = (k < p.M && p.bias) ? __bfloat162float(p.bias[k]) : 0.f;
         uint8_t* buf = outbuf + ob * OUT_BUF_BYTES;
-        // the TMA store that last read this buffer must have finished reading it
-        if (leader) { if (p.out_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-        named_bar_sync(1, 128);
+        if (p.epi_stg) {
+          // every thread has copied the previous contents of this buffer out (with two buffers the barrier of the
+          // block in between already guarantees that)
+          if (p.out_bufs == 1) named_bar_sync(1, 128);
+        } else {
+          // the TMA store that last read this buffer must have finished reading it
+          if (leader) { if (p.out_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+          named_bar_sync(1, 128);
+        }
 #pragma unroll
         for (int cc = 0; cc < BN / 32; ++cc) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (a * MB + mb) * BN + cc * 32, r);
           tmem_ld_wait();
-          uint8_t* blk = buf + (cc >> 1) * (128 * 128) + row * 128;
+          uint8_t* blk = p.y5 ? buf + (row >> 3) * (NB * 1024) + (cc >> 1) * 1024 + (row & 7) * 128
+                              : buf + (cc >> 1) * (128 * 128) + row * 128;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 v;
@@ -314,18 +340,50 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           tc_fence_before();
           mbar_arrive(&tempty[a]);
         }
-        fence_proxy_async();        // make the smem writes visible to the TMA (async proxy)
-        named_bar_sync(1, 128);
-        if (leader) {
+        if (p.epi_stg) {
+          // staged [128 ch][2 x 64 px] tile -> global: 8 consecutive threads write one full 128-B line of a channel
+          // row, so every store instruction of a warp fills 4 whole lines.  Nothing waits for the writes to land:
+          // the staging buffer is free again as soon as it has been read, and the TMA unit only serves the loads.
+          named_bar_sync(1, 128);
+          const int et = threadIdx.x - 64, g = et & 7, r0 = et >> 3;
 #pragma unroll
-          for (int j = 0; j < NB; ++j) tma_store_3d(&tmap_y, buf + j * (128 * 128), p0 + j * 64, k0, n);
-          tma_store_commit();
+          for (int j = 0; j < NB; ++j) {
+            const int px = p0 + j * 64 + g * 8;
+            if (px < p.P) {
+#pragma unroll
+              for (int rr = 0; rr < 8; ++rr) {
+                const int rw = rr * 16 + r0;
+                if (k0 + rw < p.M) {
+                  const uint4 v = *reinterpret_cast<const uint4*>(buf + j * (128 * 128) + rw * 128 + ((g ^ (rw & 7)) << 4));
+                  __stcs(reinterpret_cast<uint4*>(p.y + ((size_t)n * p.M + k0 + rw) * p.P + px), v);
+                }
+              }
+            }
+          }
+        } else {
+          fence_proxy_async();        // make the smem writes visible to the TMA (async proxy)
+          named_bar_sync(1, 128);
+          if (leader) {
+#pragma unroll
+            if (p.y5) {
+              tma_store_5d(&tmap_y, buf, 0, 0, p0 >> 6, k0 >> 3, n);
+            } else if (p.ybox == 128) {
+#pragma unroll
+              for (int j = 0; j < NB; ++j) tma_store_3d(&tmap_y, buf + j * (128 * 128), p0 + j * 64, k0, n);
+            } else {
+              for (int cg = 0; cg < 128 && k0 + cg < p.M; cg += p.ybox)
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                  tma_store_3d(&tmap_y, buf + j * (128 * 128) + cg * 128, p0 + j * 64, k0 + cg, n);
+            }
+            tma_store_commit();
+          }
         }
         if (p.out_bufs == 2) ob ^= 1;
       }
       if (++a == ACC) { a = 0; aph ^= 1; }
     }
-    if (leader) tma_store_wait_read<0>();
+    if (leader && !p.epi_stg) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
@@ -376,7 +434,7 @@ int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& t
   const int rem = budget - (p.wres ? wres_bytes : 0);
   p.out_bufs = 2;
   p.stages = (rem - 2 * OUT_BUF_BYTES) / stage_bytes;
-  if (p.stages < 3) { p.out_bufs = 1; p.stages = (rem - OUT_BUF_BYTES) / stage_bytes; }
+  if (p.stages < 3 || env_int("SPC_PW_OUTBUFS", 2) == 1) { p.out_bufs = 1; p.stages = (rem - OUT_BUF_BYTES) / stage_bytes; }
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   SPC_REQUIRE(p.stages >= 2, "tcgen05 conv: shared memory budget too small (MB=%d kchunks=%d)", MB, kchunks);
   const int smem = (p.wres ? wres_bytes : 0) + p.stages * stage_bytes + p.out_bufs * OUT_BUF_BYTES + SMEM_AUX;
@@ -400,6 +458,15 @@ int make_act_tmap(CUtensorMap* m, const void* base, int P, int Cc, int N, int bo
   const uint64_t strides[3] = {0, (uint64_t)P * 2, (uint64_t)P * Cc * 2};
   const uint32_t box[3] = {64, (uint32_t)box_rows, 1};
   return make_tmap(m, base, 3, dims, strides, box);
+}
+
+// [N][Cc][P] bf16 as (64 px, 8 channels, P/64 pixel blocks, Cc/8 channel groups, N): one box = `groups` channel
+// groups x `blocks` pixel blocks, laid out in shared memory as [group][block][8 ch][128 B]
+int make_act_tmap5(CUtensorMap* m, const void* base, int P, int Cc, int N, int groups, int blocks) {
+  const uint64_t dims[5] = {64, 8, (uint64_t)P / 64, (uint64_t)Cc / 8, (uint64_t)N};
+  const uint64_t strides[5] = {0, (uint64_t)P * 2, 128, (uint64_t)P * 16, (uint64_t)P * Cc * 2};
+  const uint32_t box[5] = {64, 8, (uint32_t)blocks, (uint32_t)groups, 1};
+  return make_tmap(m, base, 5, dims, strides, box);
 }
 
 int launch_shift_copies(const void* x, void* xs, size_t planes, int H, int W, int S, int pw, int cs, cudaStream_t st);
@@ -454,6 +521,16 @@ int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bi
     xsrc = reinterpret_cast<const __nv_bfloat16*>(xs);
   }
   CUtensorMap tw, tx, tx4, ty;
+  int xbox = (taps == 1) ? env_int("SPC_PW_XBOX", BK) : BK, ybox = env_int("SPC_PW_YBOX", 128);
+  if (xbox != 8 && xbox != 16 && xbox != 32) xbox = BK;
+  if (ybox != 8 && ybox != 16 && ybox != 32 && ybox != 64) ybox = 128;
+  // 5-d boxes (see PwParams::x5): measured on B200 (profiles/r2f_pw_box5.txt) +20..32 % on the layers whose channel
+  // planes span several 2 MB pages (104->208 @4096^2: 4.30 -> 5.67 TB/s), neutral at 1024^2 planes -> on from 4 MB planes.
+  // SPC_PW_BOX5 = 0..3 overrides (bit 0: activations, bit 1: outputs).
+  const char* box5_env = env_get("SPC_PW_BOX5");
+  const int box5 = box5_env ? atoi(box5_env) : ((size_t)P * 2 >= ((size_t)4 << 20) ? 3 : 0);
+  const int x5 = (taps == 1 && cs == 1 && (box5 & 1) && P % 64 == 0 && c.Cin % 8 == 0 && xbox == BK) ? 1 : 0;
+  const int y5 = ((box5 & 2) && P % 64 == 0 && c.M % 8 == 0 && ybox == 128) ? 1 : 0;
   {
     const uint64_t dims[2] = {(uint64_t)Cpad, (uint64_t)taps * Mpad};
     const uint64_t strides[2] = {0, (uint64_t)Cpad * 2};
@@ -471,17 +548,20 @@ int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bi
     if (rc) return rc;
     tx = tx4;
   } else {
-    rc = make_act_tmap(&tx, x, Pin, c.Cin, c.N, BK);
+    rc = x5 ? make_act_tmap5(&tx, x, Pin, c.Cin, c.N, BK / 8, BN / 64) : make_act_tmap(&tx, x, Pin, c.Cin, c.N, xbox);
     if (rc) return rc;
     tx4 = tx;
   }
-  rc = make_act_tmap(&ty, y, P, c.M, c.N, 128);
+  rc = y5 ? make_act_tmap5(&ty, y, P, c.M, c.N, 16, BN / 64) : make_act_tmap(&ty, y, P, c.M, c.N, ybox);
   if (rc) return rc;
   PwParams p{};
+  p.xbox = xbox; p.ybox = ybox; p.x5 = x5; p.y5 = y5;
   p.bias = bias; p.M = c.M; p.Cin = c.Cin; p.P = P; p.N = c.N;
   p.taps = taps; p.S = c.S; p.ph = c.ph; p.pw = c.pw; p.W = Wo; p.Mpad = Mpad;
   p.shiftN = copies ? c.N : 0;
   p.rowmul = cs;
+  p.y = y;
+  p.epi_stg = (env_int("SPC_PW_EPI_STG", 0) == 1 && P % 8 == 0 && !y5) ? 1 : 0;
   {
     const char* e = env_get("SPC_TILE_GROUP");
     p.tgroup = e ? atoi(e) : 1;   // measured: no effect on B200 (tools/stride_probe.py), kept as a knob
@@ -537,6 +617,8 @@ struct WgParams {
                     // same number of valid rows and the CTAs that share an x chunk stay in lock-step (L2 hits)
   int split_major;  // 1: concurrently running CTAs cover all (m-group, channel-block, pass) groups of the SAME
                     //    pixel range, so the dY / x chunks every group re-reads come from L2, not HBM
+  int pb;           // 64-pixel blocks per stage (1, or 2 = "wide" stages for 1x1 layers with multi-page channel planes)
+  int dy5, x5;      // wide stages: operand moves as one 5-d box [8-ch group][px block][8 ch][128 B] (see PwParams::x5)
 };
 
 template <int MG>
@@ -547,7 +629,7 @@ pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_bytes = p.nblk * 128;                        // one tap's [nblk ch][64 px] box
   const int b_slot = (b_bytes + 1023) & ~1023;
-  const int stage_bytes = MG * A_BLK_BYTES + p.TG * b_slot;
+  const int stage_bytes = p.pb * (MG * A_BLK_BYTES + p.TG * b_slot);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* tfull = empty + MAX_STAGES;
@@ -590,10 +672,32 @@ pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
         WG_DECODE(it)
         (void)mgp;
         for (int ch = c_begin; ch < c_end; ++ch) {
-          const int n = ch / p.chunks_per_image, p0 = (ch % p.chunks_per_image) * 64;
+          const int n = ch / p.chunks_per_image, p0 = (ch % p.chunks_per_image) * (64 * p.pb);
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * stage_bytes;
-          mbar_arrive_expect_tx(&full[s], MG * p.mrows * 128 + ntap * b_bytes);
+          mbar_arrive_expect_tx(&full[s], p.pb * (MG * p.mrows * 128 + ntap * b_bytes));
+          if (p.pb == 2) {   // wide stage (taps == 1): two 64-pixel blocks of every operand row
+#pragma unroll
+            for (int i = 0; i < MG; ++i) {
+              uint8_t* da = st + i * (2 * A_BLK_BYTES);
+              const int r0 = (mgp * MG + i) * p.mrows;
+              if (p.dy5) {
+                tma_load_5d(da, &tmap_dy, &full[s], 0, 0, p0 >> 6, r0 >> 3, n);
+              } else {
+                tma_load_3d(da, &tmap_dy, &full[s], p0, r0, n);
+                tma_load_3d(da + A_BLK_BYTES, &tmap_dy, &full[s], p0 + 64, r0, n);
+              }
+            }
+            uint8_t* xa = st + MG * (2 * A_BLK_BYTES);
+            if (p.x5) {
+              tma_load_5d(xa, &tmap_x, &full[s], 0, 0, p0 >> 6, (nb * p.nblk) >> 3, n);
+            } else {
+              tma_load_3d(xa, &tmap_x, &full[s], p0, nb * p.nblk, n);
+              tma_load_3d(xa + b_slot, &tmap_x, &full[s], p0 + 64, nb * p.nblk, n);
+            }
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < MG; ++i)
             tma_load_3d(st + i * A_BLK_BYTES, &tmap_dy, &full[s], p0, (mgp * MG + i) * p.mrows, n);
@@ -624,6 +728,28 @@ pw_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_consta
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          if (p.pb == 2) {
+            // wide stage: pixel block j of a 5-d box sits 1 KB after block 0 inside every 2 KB channel group; of a pair
+            // of 3-d boxes, one whole box later
+            const uint32_t sb = sa + MG * (2 * A_BLK_BYTES);
+            const uint32_t aj = p.dy5 ? 1024 : A_BLK_BYTES, asbo = p.dy5 ? 2048 : 1024;
+            const uint32_t bj = p.x5 ? 1024 : b_slot, bsbo = p.x5 ? 2048 : 1024;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t bdesc = umma_desc(sb + j * bj + ks * 32, 16, bsbo);
+#pragma unroll
+                for (int i = 0; i < MG; ++i) {
+                  const uint64_t adesc = umma_desc(sa + i * (2 * A_BLK_BYTES) + j * aj + ks * 32, 16, asbo);
+                  umma_bf16(tmem_base + i * p.nblk, adesc, bdesc, idesc, (ch > c_begin || ks > 0 || j > 0) ? 1u : 0u);
+                }
+              }
+            }
+            umma_commit(&empty[s]);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+            continue;
+          }
           const uint32_t sb = sa + MG * A_BLK_BYTES;
           for (int t = 0; t < ntap; ++t) {
 #pragma unroll
@@ -695,7 +821,7 @@ int launch_wg(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMap& 
   while (TG > 1 && MG * A_BLK_BYTES + TG * b_slot > (SMEM_LIMIT - SMEM_AUX) / 2) --TG;
   p.TG = TG;
   p.passes = (p.taps + TG - 1) / TG;
-  const int stage_bytes = MG * A_BLK_BYTES + TG * b_slot;
+  const int stage_bytes = p.pb * (MG * A_BLK_BYTES + TG * b_slot);
   p.stages = (SMEM_LIMIT - SMEM_AUX) / stage_bytes;
   if (p.stages > 6) p.stages = 6;
   p.stages = min(p.stages, env_int("SPC_WG_STAGES", p.stages));
@@ -710,8 +836,8 @@ int launch_wg(const CUtensorMap& tdy, const CUtensorMap& tx, const CUtensorMap& 
   int splits = 1;
   {
     const double clk = 1.8e9;
-    const double bytes_chunk = (double)(MG * p.mrows + p.TG * p.nblk) * 128.0;
-    const double mma_chunk = (double)MG * p.TG * 4.0 * (p.nblk > 64 ? p.nblk : 64) / 256.0 * 222.0;
+    const double bytes_chunk = (double)p.pb * (MG * p.mrows + p.TG * p.nblk) * 128.0;
+    const double mma_chunk = (double)p.pb * MG * p.TG * 4.0 * (p.nblk > 64 ? p.nblk : 64) / 256.0 * 222.0;
     const double t_chunk = (bytes_chunk / 40.0 > mma_chunk ? bytes_chunk / 40.0 : mma_chunk) / clk;
     const double elems = (double)MG * p.mrows * p.nblk * p.TG;
     const int smax = (2 * sms) / groups > 1 ? (2 * sms) / groups : 1;
@@ -759,7 +885,7 @@ pw_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
   const int half = p.nblk / 2;                                // x rows (input channels) this CTA loads
   const int b_bytes = half * 128;
   const int b_slot = (b_bytes + 1023) & ~1023;
-  const int stage_bytes = MP * A_BLK_BYTES + b_slot;
+  const int stage_bytes = p.pb * (MP * A_BLK_BYTES + b_slot);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty = full + MAX_STAGES;
   uint64_t* tfull = empty + MAX_STAGES;
@@ -785,7 +911,7 @@ pw_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
   const int ngroups = p.mgroups * p.n_blocks;                 // mgroups counts groups of MP row-PAIRS here
   const int num_items = ngroups * p.splits;
   const int per_split = (p.chunks_total + p.splits - 1) / p.splits;
-  const uint32_t stage_tx = 2u * (uint32_t)(MP * p.mrows * 128 + b_bytes);   // both CTAs' loads land on the leader's barrier
+  const uint32_t stage_tx = 2u * (uint32_t)p.pb * (uint32_t)(MP * p.mrows * 128 + b_bytes);   // both CTAs' loads land on the leader's barrier
 
 #define WGP_DECODE(it)                                                          \
   const int sp = (it) / ngroups;                                               \
@@ -802,11 +928,21 @@ pw_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
       for (int it = cluster_id; it < num_items; it += num_clusters) {
         WGP_DECODE(it)
         for (int ch = c_begin; ch < c_end; ++ch) {
-          const int n = ch / p.chunks_per_image, p0 = (ch % p.chunks_per_image) * 64;
+          const int n = ch / p.chunks_per_image, p0 = (ch % p.chunks_per_image) * (64 * p.pb);
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * stage_bytes;
           if (rank == 0) mbar_arrive_expect_tx(&full[s], stage_tx);
           else mbar_arrive_cluster(&full[s], 0);
+          if (p.pb == 2) {   // wide stage: 5-d boxes [8-ch group][2 px blocks][8 ch][128 B] (see WgParams::pb)
+#pragma unroll
+            for (int i = 0; i < MP; ++i)
+              tma_load_5d_2sm(st + i * (2 * A_BLK_BYTES), &tmap_dy, &full[s], 0, 0, p0 >> 6,
+                              (((mgp * MP + i) * 2 + (int)rank) * p.mrows) >> 3, n);
+            tma_load_5d_2sm(st + MP * (2 * A_BLK_BYTES), &tmap_x, &full[s], 0, 0, p0 >> 6,
+                            (nb * p.nblk + (int)rank * half) >> 3, n);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < MP; ++i)      // row pair (mgp*MP + i): this CTA's 128-lane half
             tma_load_3d_2sm(st + i * A_BLK_BYTES, &tmap_dy, &full[s], p0, ((mgp * MP + i) * 2 + (int)rank) * p.mrows, n);
@@ -828,6 +964,24 @@ pw_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          if (p.pb == 2) {
+            const uint32_t sb = sa + MP * (2 * A_BLK_BYTES);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t bdesc = umma_desc(sb + j * 1024 + ks * 32, 16, 2048);
+#pragma unroll
+                for (int i = 0; i < MP; ++i) {
+                  const uint64_t adesc = umma_desc(sa + i * (2 * A_BLK_BYTES) + j * 1024 + ks * 32, 16, 2048);
+                  umma_bf16_2sm(tmem_base + i * p.nblk, adesc, bdesc, idesc, (ch > c_begin || ks > 0 || j > 0) ? 1u : 0u);
+                }
+              }
+            }
+            umma_commit_2sm(&empty[s]);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+            continue;
+          }
           const uint32_t sb = sa + MP * A_BLK_BYTES;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
@@ -887,7 +1041,7 @@ pw_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_c
 template <int MP>
 int launch_wg_pair(const CUtensorMap& tdy, const CUtensorMap& tx, WgParams p, cudaStream_t st) {
   const int b_slot = ((p.nblk / 2) * 128 + 1023) & ~1023;
-  const int stage_bytes = MP * A_BLK_BYTES + b_slot;
+  const int stage_bytes = p.pb * (MP * A_BLK_BYTES + b_slot);
   p.stages = (SMEM_LIMIT - SMEM_AUX) / stage_bytes;
   if (p.stages > 6) p.stages = 6;
   p.stages = min(p.stages, env_int("SPC_WG_STAGES", p.stages));
@@ -898,8 +1052,8 @@ int launch_wg_pair(const CUtensorMap& tdy, const CUtensorMap& tx, WgParams p, cu
   int splits = 1;
   {   // same cost model as launch_wg, per CTA pair
     const double clk = 1.8e9;
-    const double bytes_chunk = (double)(MP * p.mrows + p.nblk / 2) * 128.0;          // per CTA
-    const double mma_chunk = (double)MP * 4.0 * (p.nblk > 64 ? p.nblk : 64) / 256.0 * 222.0;
+    const double bytes_chunk = (double)p.pb * (MP * p.mrows + p.nblk / 2) * 128.0;          // per CTA
+    const double mma_chunk = (double)p.pb * MP * 4.0 * (p.nblk > 64 ? p.nblk : 64) / 256.0 * 222.0;
     const double t_chunk = (bytes_chunk / 40.0 > mma_chunk ? bytes_chunk / 40.0 : mma_chunk) / clk;
     const double elems = 2.0 * MP * p.mrows * p.nblk;
     const int smax = (2 * clusters) / groups > 1 ? (2 * clusters) / groups : 1;
@@ -952,8 +1106,32 @@ int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K,
   p.mgroups = (MBtot + MG - 1) / MG;
   p.chunks_per_image = (P + 63) / 64;
   p.chunks_total = p.chunks_per_image * N;
+  p.pb = 1;
+  // CTA pairs (cta_group::2): measured on B200 (tools/wgrad_probe.py --pair, profiles/r2_wgrad_pair.txt): x1.11..1.32
+  // for >= 416 input channels (624->416 @2048^2: 4.95 -> 3.74 ms), break-even at 416->104 / 208->52, slower for
+  // the HBM-bound narrow layers (104->208: x0.75, 52->208: x0.67).  SPC_WG_2CTA=1 / SPC_WG_1CTA=1 force either.
+  const bool pair = p.taps == 1 && (env_get("SPC_WG_2CTA") ? true : (env_get("SPC_WG_1CTA") ? false : C >= 400)) &&
+                    MBtot >= 2 && p.nblk % 16 == 0;
+  // wide stages (two 64-pixel blocks per operand row and stage, 5-d boxes): for 1x1 layers whose channel planes span
+  // several 2 MB pages, same reason as PwParams::x5.  SPC_WG_WIDE=0/1 overrides, SPC_WG_BOX5 (bit 0 dy, bit 1 x).
+  {
+    const char* we = env_get("SPC_WG_WIDE");
+    const bool wide = p.taps == 1 && !pair && P % 128 == 0 && (we ? atoi(we) != 0 : (size_t)P * 2 >= ((size_t)2 << 20));
+    if (wide) {
+      const int b_slot = (p.nblk * 128 + 1023) & ~1023;
+      while (MG > 1 && 2 * 2 * (MG * A_BLK_BYTES + b_slot) > SMEM_LIMIT - SMEM_AUX) MG >>= 1;
+      p.mgroups = (MBtot + MG - 1) / MG;
+      p.pb = 2;
+      p.chunks_per_image = P / 128;
+      p.chunks_total = p.chunks_per_image * N;
+      const char* be = env_get("SPC_WG_BOX5");
+      const int b5 = be ? atoi(be) : 3;
+      p.dy5 = ((b5 & 1) && K % 8 == 0 && p.mrows % 8 == 0) ? 1 : 0;
+      p.x5 = ((b5 & 2) && C % 8 == 0 && p.nblk % 8 == 0) ? 1 : 0;
+    }
+  }
   CUtensorMap tdy, tx, tx4;
-  int rc = make_act_tmap(&tdy, dy, P, K, N, p.mrows);
+  int rc = p.dy5 ? make_act_tmap5(&tdy, dy, P, K, N, p.mrows / 8, 2) : make_act_tmap(&tdy, dy, P, K, N, p.mrows);
   if (rc) return rc;
   if (p.taps > 1) {
     const uint64_t dims[4] = {(uint64_t)Wo, (uint64_t)Hin, (uint64_t)C, (uint64_t)N * (copies ? S : 1)};
@@ -963,24 +1141,37 @@ int run_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* dy, float* dw, int K,
     if (rc) return rc;
     tx = tx4;
   } else {
-    rc = make_act_tmap(&tx, x, P, C, N, p.nblk);
+    rc = p.x5 ? make_act_tmap5(&tx, x, P, C, N, p.nblk / 8, 2) : make_act_tmap(&tx, x, P, C, N, p.nblk);
     if (rc) return rc;
     tx4 = tx;
   }
-  // CTA pairs (cta_group::2): measured on B200 (tools/wgrad_probe.py --pair, profiles/r2_wgrad_pair.txt): x1.11..1.32
-  // for >= 416 input channels (624->416 @2048^2: 4.95 -> 3.74 ms), break-even at 416->104 / 208->52, slower for
-  // the HBM-bound narrow layers (104->208: x0.75, 52->208: x0.67).  SPC_WG_2CTA=1 / SPC_WG_1CTA=1 force either.
-  const bool pair = env_get("SPC_WG_2CTA") ? true : (env_get("SPC_WG_1CTA") ? false : C >= 400);
-  if (p.taps == 1 && pair && MBtot >= 2 && p.nblk % 16 == 0) {
-    // CTA pairs (experimental, see pw_wgrad_pair_kernel): row pairs of 2*mrows, MP pairs per item
+  if (pair) {
+    // CTA pairs (see pw_wgrad_pair_kernel): row pairs of 2*mrows, MP pairs per item.  Wide stages (5-d boxes, see
+    // WgParams::pb) measured x1.34..1.64 on every pair layer of the list (profiles/r2f_wgrad_pairwide.txt:
+    // 1664->416 @1024^2 2.05 -> 1.53 ms = 948 TFLOP/s, 624->416 @2048^2 4.05 -> 2.54 ms); SPC_WG_PAIR_WIDE=0/1 overrides.
     const int npairs = (MBtot + 1) / 2;
     int MP = 512 / p.nblk;
     if (MP > npairs) MP = npairs;
     MP = MP >= 2 ? 2 : 1;
-    p.mgroups = (npairs + MP - 1) / MP;
     CUtensorMap txh;      // x boxes of nblk/2 channels: each CTA of a pair loads its half of the block
-    rc = make_act_tmap(&txh, x, P, C, N, p.nblk / 2);
+    const char* we = env_get("SPC_WG_PAIR_WIDE");
+    const bool wide = P % 128 == 0 && K % 8 == 0 && C % 8 == 0 && p.mrows % 8 == 0 && p.nblk % 16 == 0 &&
+                      (we ? atoi(we) != 0 : (size_t)P * 2 >= ((size_t)2 << 20));
+    if (wide) {
+      const int b_slot = ((p.nblk / 2) * 128 + 1023) & ~1023;
+      if (MP == 2 && env_get("SPC_WG_PAIR_MP1")) MP = 1;
+      while (MP > 1 && 2 * 2 * (MP * A_BLK_BYTES + b_slot) > SMEM_LIMIT - SMEM_AUX) MP >>= 1;
+      p.pb = 2;
+      p.chunks_per_image = P / 128;
+      p.chunks_total = p.chunks_per_image * N;
+      rc = make_act_tmap5(&tdy, dy, P, K, N, p.mrows / 8, 2);
+      if (rc) return rc;
+      rc = make_act_tmap5(&txh, x, P, C, N, p.nblk / 16, 2);
+    } else {
+      rc = make_act_tmap(&txh, x, P, C, N, p.nblk / 2);
+    }
     if (rc) return rc;
+    p.mgroups = (npairs + MP - 1) / MP;
     return MP == 2 ? launch_wg_pair<2>(tdy, txh, p, st) : launch_wg_pair<1>(tdy, txh, p, st);
   }
   if (MG == 1) return launch_wg<1>(tdy, tx, tx4, p, st);

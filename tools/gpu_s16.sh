@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 240 python tools/pw_probe.py > gpurun_out/r2f_pw_probe.log 2>&1; echo "pw probe rc=$?"; cat gpurun_out/r2f_pw_probe.log

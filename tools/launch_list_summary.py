@@ -21,7 +21,7 @@ def main():
     for r in rows[1:]:
         if len(r) <= iv:
             continue
-        name = re.sub(r"\(.*", "", r[ik]).replace("void ", "").replace("(anonymous namespace)::", "").replace("unnamed>::", "")
+        name = re.sub(r"\(.*", "", r[ik]).replace("void ", "").replace("(anonymous namespace)::", "").replace("unnamed>::", "").replace("spc::<", "").replace("spc::", "")
         if any(o in name for o in FOREIGN):
             continue
         v = float(r[iv].replace(",", ""))

@@ -6,7 +6,8 @@ from mpi4dl_b200 import _lib
 from mpi4dl_b200.torchgems.spatial import _ConvSpatialFn
 dev = "cuda:0"
 for (N, C, K, H, W) in [(1, 104, 208, 4096, 4096), (16, 104, 208, 1024, 1024), (256, 104, 208, 256, 256), (4096, 104, 208, 64, 64),
-                         (1, 208, 52, 4096, 4096), (256, 208, 52, 256, 256)]:
+                         (1, 208, 52, 4096, 4096), (256, 208, 52, 256, 256), (64, 104, 208, 512, 512), (1, 416, 104, 1024, 1024), (16, 416, 104, 256, 256),
+                         (64, 416, 104, 128, 128), (1, 416, 416, 1024, 1024), (64, 416, 416, 128, 128)]:
     x = torch.randn(N, C, H, W, device=dev).to(torch.bfloat16)
     w = (torch.randn(K, C, 1, 1, device=dev) / C ** 0.5).to(torch.bfloat16)
     desc = (N, C, H, W, K, 1, 1, 1, 1, 0, 0, _lib.SPC_BF16, _lib.SPC_ALGO_TCGEN05)

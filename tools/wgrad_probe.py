@@ -38,6 +38,17 @@ def main():
         CONFIGS = [{}] + [dict(SPC_WG_SPLITS=str(v)) for v in (148, 74, 37, 18, 296)]
         SHAPES = [(416, 416, 1024), (1664, 416, 1024), (104, 416, 1024), (104, 416, 360), (416, 416, 360), (416, 104, 360),
                   (104, 208, 4096), (1248, 416, 360)]
+    if "--wide" in sys.argv:
+        # wide stages (two 64-pixel blocks per stage, 5-d TMA boxes) for layers with multi-page channel planes
+        CONFIGS = [dict(SPC_WG_WIDE="0"), {}, dict(SPC_WG_WIDE="1", SPC_WG_BOX5="0"), dict(SPC_WG_WIDE="1", SPC_WG_BOX5="1"),
+                   dict(SPC_WG_WIDE="1", SPC_WG_BOX5="2"), dict(SPC_WG_WIDE="1", SPC_WG_MG="1")]
+        SHAPES = [(104, 208, 4096), (208, 52, 4096), (52, 208, 2048), (208, 208, 2048), (104, 416, 1024), (208, 104, 1024)]
+        KNOBS.extend(["SPC_WG_WIDE", "SPC_WG_BOX5"])
+    if "--pairwide" in sys.argv:
+        CONFIGS = [{}, dict(SPC_WG_PAIR_WIDE="1"), dict(SPC_WG_PAIR_WIDE="1", SPC_WG_PAIR_MP1="1")]
+        SHAPES = [(416, 416, 1024), (1664, 416, 1024), (624, 416, 2048), (1248, 416, 1024), (624, 208, 2048), (416, 104, 2048),
+                  (416, 104, 1024), (104, 416, 1024)]
+        KNOBS.extend(["SPC_WG_PAIR_WIDE", "SPC_WG_PAIR_MP1"])
     if "--pair" in sys.argv:
         # first run of the cta_group::2 kernel (never executed on hardware in round 1): ALWAYS under an outer
         # `timeout 90`, results are compared with the single-CTA kernel's dw (MISMATCH flag)
