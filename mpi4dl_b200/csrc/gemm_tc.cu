@@ -118,8 +118,8 @@ __global__ void repack_weights_kernel(const __nv_bfloat16* __restrict__ w, __nv_
 }
 
 // ---- fprop / dgrad kernel -----------------------------------------------------------------------
-constexpr int BN = 128;                       // pixels per tile (two 64-pixel swizzle blocks)
-constexpr int OUT_BUF_BYTES = 128 * BN * 2;   // epilogue staging: one 128-channel block of a tile
+constexpr int BN_DEFAULT = 128;               // pixels per tile (two 64-pixel swizzle blocks); 256 in the wide-N variant
+constexpr int OUT_BUF_BYTES = 128 * 128 * 2;  // epilogue staging: one 128-channel block of 128 pixels of a tile
 constexpr int MAX_STAGES = 8;
 
 struct PwParams {
@@ -145,11 +145,12 @@ struct PwParams {
                                // (8-channel group, 64-pixel block, channel, pixel): the TMA unit touches 8 channel
                                // planes (2 MB pages each) at a time and visits both pixel blocks of each before moving
                                // on, instead of walking 64 / 128 planes per pixel block (address-translation reach)
+  int stationary_ok;           // host: stationary weights allowed with several output-channel groups
   int xbox, ybox;              // channel rows per TMA load / store box (64 / 128 = one box per 64-pixel block; smaller
                                // boxes walk FEWER channel planes -- 2 MB pages -- between the two pixel blocks of a tile)
 };
 
-template <int MB>
+template <int MB, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                const __grid_constant__ CUtensorMap tmap_x4, const __grid_constant__ CUtensorMap tmap_y,
@@ -193,13 +194,18 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     if (lane == 0) {
       tma_prefetch_desc(&tmap_w);
       tma_prefetch_desc(&tmap_x);
-      if (p.wres) {   // weights-stationary: every CTA keeps the whole (padded) filter in smem
+      if (p.wres) {
+        // weights-stationary: the CTA keeps the (padded) filter rows of ITS group of output channels in smem for its
+        // whole life.  With several groups the grid is a multiple of num_mg, so tile t = it * grid + blockIdx.x
+        // always lands in group blockIdx.x % num_mg (t % num_mg below), and the CTAs of the other groups read the same
+        // activation tile at about the same time (L2 hits).
+        const int mg0 = blockIdx.x % p.num_mg;
         mbar_arrive_expect_tx(wfull, wres_bytes);
-        for (int it = 0; it < iters; ++it)   // wres implies num_mg == 1
+        for (int it = 0; it < iters; ++it)
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb)
             tma_load_2d(wres + (it * MB + mb) * A_BLK_BYTES, &tmap_w, wfull, (it % kchunks) * BK,
-                        (it / kchunks) * p.Mpad + mb * 128);
+                        (it / kchunks) * p.Mpad + mg0 * (MB * 128) + mb * 128);
       }
       int s = 0, ph = 0;
       for (int it = 0;; ++it) {
@@ -308,78 +314,81 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         if (k0 >= p.M) break;                       // block-uniform: nothing valid in this block
         const int k = k0 + row;
         const float bias = (k < p.M && p.bias) ? __bfloat162float(p.bias[k]) : 0.f;
-        uint8_t* buf = outbuf + ob * OUT_BUF_BYTES;
-        if (p.epi_stg) {
-          // every thread has copied the previous contents of this buffer out (with two buffers the barrier of the
-          // block in between already guarantees that)
-          if (p.out_bufs == 1) named_bar_sync(1, 128);
-        } else {
-          // the TMA store that last read this buffer must have finished reading it
-          if (leader) { if (p.out_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-          named_bar_sync(1, 128);
-        }
-#pragma unroll
-        for (int cc = 0; cc < BN / 32; ++cc) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (a * MB + mb) * BN + cc * 32, r);
-          tmem_ld_wait();
-          uint8_t* blk = p.y5 ? buf + (row >> 3) * (NB * 1024) + (cc >> 1) * 1024 + (row & 7) * 128
-                              : buf + (cc >> 1) * (128 * 128) + row * 128;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(r[8 * q + 0]) + bias, __uint_as_float(r[8 * q + 1]) + bias);
-            v.y = pack_bf16x2(__uint_as_float(r[8 * q + 2]) + bias, __uint_as_float(r[8 * q + 3]) + bias);
-            v.z = pack_bf16x2(__uint_as_float(r[8 * q + 4]) + bias, __uint_as_float(r[8 * q + 5]) + bias);
-            v.w = pack_bf16x2(__uint_as_float(r[8 * q + 6]) + bias, __uint_as_float(r[8 * q + 7]) + bias);
-            const int chunk = ((cc & 1) * 4 + q) ^ (row & 7);   // SWIZZLE_128B: 16-B chunk ^ (row % 8)
-            *reinterpret_cast<uint4*>(blk + chunk * 16) = v;
+#pragma unroll 1
+        for (int h = 0; h < BN / 128; ++h) {        // 128 pixels (two 64-pixel blocks) of the tile at a time
+          const int ph0 = p0 + h * 128;
+          uint8_t* buf = outbuf + ob * OUT_BUF_BYTES;
+          if (p.epi_stg) {
+            // every thread has copied the previous contents of this buffer out (with two buffers the barrier of the
+            // block in between already guarantees that)
+            if (p.out_bufs == 1) named_bar_sync(1, 128);
+          } else {
+            // the TMA store that last read this buffer must have finished reading it
+            if (leader) { if (p.out_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+            named_bar_sync(1, 128);
           }
-        }
-        if (mb == MB - 1 || k0 + 128 >= p.M) {   // last block of this tile read: release the accumulator
-          tc_fence_before();
-          mbar_arrive(&tempty[a]);
-        }
-        if (p.epi_stg) {
-          // staged [128 ch][2 x 64 px] tile -> global: 8 consecutive threads write one full 128-B line of a channel
-          // row, so every store instruction of a warp fills 4 whole lines.  Nothing waits for the writes to land:
-          // the staging buffer is free again as soon as it has been read, and the TMA unit only serves the loads.
-          named_bar_sync(1, 128);
-          const int et = threadIdx.x - 64, g = et & 7, r0 = et >> 3;
 #pragma unroll
-          for (int j = 0; j < NB; ++j) {
-            const int px = p0 + j * 64 + g * 8;
-            if (px < p.P) {
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (a * MB + mb) * BN + h * 128 + cc * 32, r);
+            tmem_ld_wait();
+            uint8_t* blk = p.y5 ? buf + (row >> 3) * 2048 + (cc >> 1) * 1024 + (row & 7) * 128
+                                : buf + (cc >> 1) * (128 * 128) + row * 128;
 #pragma unroll
-              for (int rr = 0; rr < 8; ++rr) {
-                const int rw = rr * 16 + r0;
-                if (k0 + rw < p.M) {
-                  const uint4 v = *reinterpret_cast<const uint4*>(buf + j * (128 * 128) + rw * 128 + ((g ^ (rw & 7)) << 4));
-                  __stcs(reinterpret_cast<uint4*>(p.y + ((size_t)n * p.M + k0 + rw) * p.P + px), v);
+            for (int q = 0; q < 4; ++q) {
+              uint4 v;
+              v.x = pack_bf16x2(__uint_as_float(r[8 * q + 0]) + bias, __uint_as_float(r[8 * q + 1]) + bias);
+              v.y = pack_bf16x2(__uint_as_float(r[8 * q + 2]) + bias, __uint_as_float(r[8 * q + 3]) + bias);
+              v.z = pack_bf16x2(__uint_as_float(r[8 * q + 4]) + bias, __uint_as_float(r[8 * q + 5]) + bias);
+              v.w = pack_bf16x2(__uint_as_float(r[8 * q + 6]) + bias, __uint_as_float(r[8 * q + 7]) + bias);
+              const int chunk = ((cc & 1) * 4 + q) ^ (row & 7);   // SWIZZLE_128B: 16-B chunk ^ (row % 8)
+              *reinterpret_cast<uint4*>(blk + chunk * 16) = v;
+            }
+          }
+          if (h == BN / 128 - 1 && (mb == MB - 1 || k0 + 128 >= p.M)) {   // last read of this tile's accumulators
+            tc_fence_before();
+            mbar_arrive(&tempty[a]);
+          }
+          if (p.epi_stg) {
+            // staged [128 ch][2 x 64 px] tile -> global: 8 consecutive threads write one full 128-B line of a channel
+            // row, so every store instruction of a warp fills 4 whole lines.  Nothing waits for the writes to land:
+            // the staging buffer is free again as soon as it has been read, and the TMA unit only serves the loads.
+            named_bar_sync(1, 128);
+            const int et = threadIdx.x - 64, g = et & 7, r0 = et >> 3;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int px = ph0 + j * 64 + g * 8;
+              if (px < p.P) {
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                  const int rw = rr * 16 + r0;
+                  if (k0 + rw < p.M) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(buf + j * (128 * 128) + rw * 128 + ((g ^ (rw & 7)) << 4));
+                    __stcs(reinterpret_cast<uint4*>(p.y + ((size_t)n * p.M + k0 + rw) * p.P + px), v);
+                  }
                 }
               }
             }
-          }
-        } else {
-          fence_proxy_async();        // make the smem writes visible to the TMA (async proxy)
-          named_bar_sync(1, 128);
-          if (leader) {
+          } else {
+            fence_proxy_async();        // make the smem writes visible to the TMA (async proxy)
+            named_bar_sync(1, 128);
+            if (leader) {
+              if (p.y5) {
+                tma_store_5d(&tmap_y, buf, 0, 0, ph0 >> 6, k0 >> 3, n);
+              } else if (p.ybox == 128) {
 #pragma unroll
-            if (p.y5) {
-              tma_store_5d(&tmap_y, buf, 0, 0, p0 >> 6, k0 >> 3, n);
-            } else if (p.ybox == 128) {
+                for (int j = 0; j < 2; ++j) tma_store_3d(&tmap_y, buf + j * (128 * 128), ph0 + j * 64, k0, n);
+              } else {
+                for (int cg = 0; cg < 128 && k0 + cg < p.M; cg += p.ybox)
 #pragma unroll
-              for (int j = 0; j < NB; ++j) tma_store_3d(&tmap_y, buf + j * (128 * 128), p0 + j * 64, k0, n);
-            } else {
-              for (int cg = 0; cg < 128 && k0 + cg < p.M; cg += p.ybox)
-#pragma unroll
-                for (int j = 0; j < NB; ++j)
-                  tma_store_3d(&tmap_y, buf + j * (128 * 128) + cg * 128, p0 + j * 64, k0 + cg, n);
+                  for (int j = 0; j < 2; ++j)
+                    tma_store_3d(&tmap_y, buf + j * (128 * 128) + cg * 128, ph0 + j * 64, k0 + cg, n);
+              }
+              tma_store_commit();
             }
-            tma_store_commit();
           }
+          if (p.out_bufs == 2) ob ^= 1;
         }
-        if (p.out_bufs == 2) ob ^= 1;
       }
       if (++a == ACC) { a = 0; aph ^= 1; }
     }
@@ -423,13 +432,23 @@ inline int sm_count() {
 constexpr int SMEM_LIMIT = 222 * 1024;   // leave room for a small co-resident kernel (halo post/collect, boundary strips)
 constexpr int SMEM_AUX = 1024 /*align*/ + 512 /*barriers*/;
 
-template <int MB>
+template <int MB, int BN>
 int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& tx4, const CUtensorMap& ty, PwParams p,
               cudaStream_t st) {
   const int kchunks = (p.Cin + BK - 1) / BK;
   const int budget = SMEM_LIMIT - SMEM_AUX;
   const int wres_bytes = p.taps * kchunks * MB * A_BLK_BYTES;
-  p.wres = (p.num_mg == 1 && wres_bytes <= 128 * 1024) ? 1 : 0;
+  const int sms = sm_count();
+  int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  if (p.num_tiles < 16 * sms) p.tgroup = 1;   // small problems: keep every SM busy
+  // stationary weights with several groups of output channels: every CTA serves one group (see the kernel), which needs
+  // a grid that is a multiple of num_mg and tiles dealt round-robin
+  bool stationary = wres_bytes <= 128 * 1024;
+  if (stationary && p.num_mg > 1) {
+    if (p.stationary_ok && grid >= 4 * p.num_mg) { grid = grid / p.num_mg * p.num_mg; p.tgroup = 1; }
+    else stationary = false;
+  }
+  p.wres = stationary ? 1 : 0;
   const int stage_bytes = (p.wres ? 0 : MB * A_BLK_BYTES) + (BN / 64) * B_BLK_BYTES;
   const int rem = budget - (p.wres ? wres_bytes : 0);
   p.out_bufs = 2;
@@ -438,15 +457,12 @@ int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& t
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   SPC_REQUIRE(p.stages >= 2, "tcgen05 conv: shared memory budget too small (MB=%d kchunks=%d)", MB, kchunks);
   const int smem = (p.wres ? wres_bytes : 0) + p.stages * stage_bytes + p.out_bufs * OUT_BUF_BYTES + SMEM_AUX;
-  auto kern = pw_gemm_kernel<MB>;
+  auto kern = pw_gemm_kernel<MB, BN>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
-  const int sms = sm_count();
-  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  if (p.num_tiles < 16 * sms) p.tgroup = 1;   // small problems: keep every SM busy
   kern<<<grid, TC_THREADS, smem, st>>>(tw, tx, tx4, ty, p);
   count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
@@ -521,6 +537,17 @@ int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bi
     xsrc = reinterpret_cast<const __nv_bfloat16*>(xs);
   }
   CUtensorMap tw, tx, tx4, ty;
+  // Wide-N variant (256-pixel tiles, one 128-row block of output channels per CTA with its filter rows resident in
+  // shared memory, double-buffered accumulators): for pointwise layers with 3+ blocks of output channels and 256..512
+  // input channels, which are bound by the tensor pipe -- a 128x128x16 MMA costs almost what a 128x256x16 one does
+  // (measured 185-270 vs 222 clk), so N = 256 should nearly halve the MMA time per pixel.  MEASURED (profiles/
+  // r2h_pw_n256.txt): slower, 416->416 @1024^2 0.56 -> 0.65 ms -- with the filter rows resident only two 32 KB
+  // activation stages fit, and 64 KB in flight per SM at ~2 us of load latency caps the CTA at ~35 GB/s.  Kept behind
+  // SPC_PW_N256=1 (off by default); results are bit-identical to the default path.
+  const char* n256_env = env_get("SPC_PW_N256");
+  const bool n256 = taps == 1 && cs == 1 && Mpad / 128 >= 3 && (Cpad / BK) * A_BLK_BYTES <= 128 * 1024 && P % 256 == 0 &&
+                    (n256_env ? atoi(n256_env) != 0 : false);
+  const int BN = n256 ? 256 : BN_DEFAULT;
   int xbox = (taps == 1) ? env_int("SPC_PW_XBOX", BK) : BK, ybox = env_int("SPC_PW_YBOX", 128);
   if (xbox != 8 && xbox != 16 && xbox != 32) xbox = BK;
   if (ybox != 8 && ybox != 16 && ybox != 32 && ybox != 64) ybox = 128;
@@ -552,7 +579,7 @@ int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bi
     if (rc) return rc;
     tx4 = tx;
   }
-  rc = y5 ? make_act_tmap5(&ty, y, P, c.M, c.N, 16, BN / 64) : make_act_tmap(&ty, y, P, c.M, c.N, ybox);
+  rc = y5 ? make_act_tmap5(&ty, y, P, c.M, c.N, 16, 2) : make_act_tmap(&ty, y, P, c.M, c.N, ybox);
   if (rc) return rc;
   PwParams p{};
   p.xbox = xbox; p.ybox = ybox; p.x5 = x5; p.y5 = y5;
@@ -574,14 +601,26 @@ int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bi
   // Measured (r1, profiles/): wins for Cin <= 416 (+6..19 %), loses for Cin >= 624 where the K loop is
   // long enough to hide the epilogue and the extra activation reads cost more than the overlap gains.
   int mb = MBtot >= 3 ? (c.Cin <= 512 ? 2 : 4) : MBtot;
-  if (MBtot >= 3 && env_get("SPC_PW_MB4")) mb = 4;                 // A/B knobs
-  if (MBtot >= 3 && env_get("SPC_PW_MB2")) mb = 2;
+  // Stationary weights with several groups of output channels on 128-pixel tiles (SPC_PW_STATIONARY=1, off by default):
+  // measured SLOWER than streaming them (416->416 @1024^2: 0.56 -> 0.83 ms, profiles/r2h_pw_stationary.txt) -- with
+  // one block per CTA the tensor pipe issues half as many MACs per MMA slot.  The wide-N variant above is the one
+  // that pays.
+  {
+    const char* se = env_get("SPC_PW_STATIONARY");
+    const int kch = (c.Cin + BK - 1) / BK;
+    p.stationary_ok = ((se && atoi(se) != 0) || n256) && taps * kch * A_BLK_BYTES <= 128 * 1024;
+    if (p.stationary_ok && MBtot >= 3 && !n256) mb = (taps * kch * 2 * A_BLK_BYTES <= 128 * 1024) ? 2 : 1;
+    if (n256) mb = 1;
+  }
+  if (MBtot >= 3 && !n256 && env_get("SPC_PW_MB4")) mb = 4;                 // A/B knobs
+  if (MBtot >= 3 && !n256 && env_get("SPC_PW_MB2")) mb = 2;
   p.num_mg = (MBtot + mb - 1) / mb;
   p.tiles_per_image = (P + BN - 1) / BN;
   p.num_tiles = p.tiles_per_image * c.N * p.num_mg;
-  if (mb == 1) return launch_pw<1>(tw, tx, tx4, ty, p, st);
-  if (mb == 2) return launch_pw<2>(tw, tx, tx4, ty, p, st);
-  return launch_pw<4>(tw, tx, tx4, ty, p, st);
+  if (n256) return launch_pw<1, 256>(tw, tx, tx4, ty, p, st);
+  if (mb == 1) return launch_pw<1, 128>(tw, tx, tx4, ty, p, st);
+  if (mb == 2) return launch_pw<2, 128>(tw, tx, tx4, ty, p, st);
+  return launch_pw<4, 128>(tw, tx, tx4, ty, p, st);
 }
 
 // pointwise helper (1x1): Y[N][M][P] = Wp[M x Cin] * X[N][Cin][P]

@@ -14,7 +14,12 @@ from mpi4dl_b200 import _lib  # noqa: E402
 SHAPES = [(104, 208, 4096, 4096), (208, 52, 4096, 4096), (52, 208, 2048, 2048), (416, 104, 1024, 1024), (104, 416, 1024, 1024),
           (416, 416, 1024, 1024), (1664, 416, 1024, 1024), (624, 416, 2048, 2048), (208, 208, 2048, 2048), (52, 52, 1000, 1096)]
 CONFIGS = [{}, dict(SPC_PW_EPI_STG="1"), dict(SPC_PW_EPI_STG="1", SPC_PW_OUTBUFS="1"), dict(SPC_PW_OUTBUFS="1")]
-KNOBS = ["SPC_PW_EPI_STG", "SPC_PW_OUTBUFS", "SPC_PW_XBOX", "SPC_PW_YBOX", "SPC_PW_BOX5"]
+KNOBS = ["SPC_PW_EPI_STG", "SPC_PW_OUTBUFS", "SPC_PW_XBOX", "SPC_PW_YBOX", "SPC_PW_BOX5", "SPC_PW_STATIONARY", "SPC_PW_MB2", "SPC_PW_N256"]
+if "--stationary" in sys.argv:
+    # weights resident per CTA with several groups of output channels (first line = the previous behaviour)
+    CONFIGS = [dict(SPC_PW_N256="0"), {}, dict(SPC_PW_BOX5="3"), dict(SPC_PW_N256="1"), dict(SPC_PW_N256="0", SPC_PW_STATIONARY="1")]
+    SHAPES = [(416, 416, 1024, 1024), (104, 416, 1024, 1024), (416, 104, 1024, 1024), (1664, 416, 1024, 1024), (1248, 416, 1024, 1024),
+              (624, 416, 2048, 2048), (416, 416, 360, 1024), (104, 208, 4096, 4096)]
 if "--boxes" in sys.argv:
     # channel rows per TMA box: fewer planes (2 MB pages) walked between the two 64-pixel blocks of a tile
     CONFIGS = [{}, dict(SPC_PW_BOX5="1"), dict(SPC_PW_BOX5="2"), dict(SPC_PW_BOX5="3"), dict(SPC_PW_XBOX="16"), dict(SPC_PW_YBOX="16")]
