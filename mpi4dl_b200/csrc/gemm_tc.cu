@@ -150,7 +150,10 @@ struct PwParams {
                                // boxes walk FEWER channel planes -- 2 MB pages -- between the two pixel blocks of a tile)
 };
 
-template <int MB, int BN>
+// EXT = false compiles the round-2 options (5-d boxes, box-row knobs, per-thread-store epilogue) out: the launches that
+// use none of them (every tap-mode launch; the stem is epilogue-bound and ran 16 % slower with the extra branches in
+// its epilogue, A/B on one GPU) get exactly the plain kernel.
+template <int MB, int BN, bool EXT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                const __grid_constant__ CUtensorMap tmap_x4, const __grid_constant__ CUtensorMap tmap_y,
@@ -176,6 +179,8 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool x5 = EXT && p.x5, y5 = EXT && p.y5, epi_stg = EXT && p.epi_stg;
+  const int xbox = EXT ? p.xbox : BK, ybox = EXT ? p.ybox : 128;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -228,13 +233,13 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             st += MB * A_BLK_BYTES;
           }
           if (p.taps == 1) {
-            if (p.x5) {
+            if (x5) {
               tma_load_5d(st, &tmap_x, &full[s], 0, 0, p0 >> 6, kc * (BK / 8), n);
-            } else if (p.xbox == BK) {
+            } else if (xbox == BK) {
 #pragma unroll
               for (int j = 0; j < NB; ++j) tma_load_3d(st + j * B_BLK_BYTES, &tmap_x, &full[s], p0 + j * 64, kc * BK, n);
             } else {
-              for (int cg = 0; cg < BK; cg += p.xbox)
+              for (int cg = 0; cg < BK; cg += xbox)
 #pragma unroll
                 for (int j = 0; j < NB; ++j)
                   tma_load_3d(st + j * B_BLK_BYTES + cg * 128, &tmap_x, &full[s], p0 + j * 64, kc * BK + cg, n);
@@ -276,7 +281,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
           for (int ks = 0; ks < nsteps; ++ks) {
             // B: MN-major SW128. 16 channels = two 8-row groups (SBO = 1024 B); 64-px blocks at LBO = 8 KB
             // (5-d box layout [8-ch group][px block][8 ch][128 B]: px blocks at LBO = 1 KB, channel groups at SBO = 2 KB)
-            const uint64_t bdesc = p.x5 ? umma_desc(sb + ks * (NB * 2048), 1024, NB * 1024)
+            const uint64_t bdesc = x5 ? umma_desc(sb + ks * (NB * 2048), 1024, NB * 1024)
                                         : umma_desc(sb + ks * 2048, B_BLK_BYTES, 1024);
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
@@ -318,7 +323,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         for (int h = 0; h < BN / 128; ++h) {        // 128 pixels (two 64-pixel blocks) of the tile at a time
           const int ph0 = p0 + h * 128;
           uint8_t* buf = outbuf + ob * OUT_BUF_BYTES;
-          if (p.epi_stg) {
+          if (epi_stg) {
             // every thread has copied the previous contents of this buffer out (with two buffers the barrier of the
             // block in between already guarantees that)
             if (p.out_bufs == 1) named_bar_sync(1, 128);
@@ -332,7 +337,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (a * MB + mb) * BN + h * 128 + cc * 32, r);
             tmem_ld_wait();
-            uint8_t* blk = p.y5 ? buf + (row >> 3) * 2048 + (cc >> 1) * 1024 + (row & 7) * 128
+            uint8_t* blk = y5 ? buf + (row >> 3) * 2048 + (cc >> 1) * 1024 + (row & 7) * 128
                                 : buf + (cc >> 1) * (128 * 128) + row * 128;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -349,7 +354,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             tc_fence_before();
             mbar_arrive(&tempty[a]);
           }
-          if (p.epi_stg) {
+          if (epi_stg) {
             // staged [128 ch][2 x 64 px] tile -> global: 8 consecutive threads write one full 128-B line of a channel
             // row, so every store instruction of a warp fills 4 whole lines.  Nothing waits for the writes to land:
             // the staging buffer is free again as soon as it has been read, and the TMA unit only serves the loads.
@@ -373,13 +378,13 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             fence_proxy_async();        // make the smem writes visible to the TMA (async proxy)
             named_bar_sync(1, 128);
             if (leader) {
-              if (p.y5) {
+              if (y5) {
                 tma_store_5d(&tmap_y, buf, 0, 0, ph0 >> 6, k0 >> 3, n);
-              } else if (p.ybox == 128) {
+              } else if (ybox == 128) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) tma_store_3d(&tmap_y, buf + j * (128 * 128), ph0 + j * 64, k0, n);
               } else {
-                for (int cg = 0; cg < 128 && k0 + cg < p.M; cg += p.ybox)
+                for (int cg = 0; cg < 128 && k0 + cg < p.M; cg += ybox)
 #pragma unroll
                   for (int j = 0; j < 2; ++j)
                     tma_store_3d(&tmap_y, buf + j * (128 * 128) + cg * 128, ph0 + j * 64, k0 + cg, n);
@@ -392,7 +397,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
       }
       if (++a == ACC) { a = 0; aph ^= 1; }
     }
-    if (leader && !p.epi_stg) tma_store_wait_read<0>();
+    if (leader && !epi_stg) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
@@ -432,8 +437,8 @@ inline int sm_count() {
 constexpr int SMEM_LIMIT = 222 * 1024;   // leave room for a small co-resident kernel (halo post/collect, boundary strips)
 constexpr int SMEM_AUX = 1024 /*align*/ + 512 /*barriers*/;
 
-template <int MB, int BN>
-int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& tx4, const CUtensorMap& ty, PwParams p,
+template <int MB, int BN, bool EXT>
+int launch_pw_ext(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& tx4, const CUtensorMap& ty, PwParams p,
               cudaStream_t st) {
   const int kchunks = (p.Cin + BK - 1) / BK;
   const int budget = SMEM_LIMIT - SMEM_AUX;
@@ -457,7 +462,7 @@ int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& t
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   SPC_REQUIRE(p.stages >= 2, "tcgen05 conv: shared memory budget too small (MB=%d kchunks=%d)", MB, kchunks);
   const int smem = (p.wres ? wres_bytes : 0) + p.stages * stage_bytes + p.out_bufs * OUT_BUF_BYTES + SMEM_AUX;
-  auto kern = pw_gemm_kernel<MB, BN>;
+  auto kern = pw_gemm_kernel<MB, BN, EXT>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     SPC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -467,6 +472,13 @@ int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& t
   count_launch();
   SPC_CHECK_CUDA(cudaGetLastError());
   return SPC_OK;
+}
+
+template <int MB, int BN>
+int launch_pw(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& tx4, const CUtensorMap& ty, const PwParams& p,
+              cudaStream_t st) {
+  const bool ext = p.x5 || p.y5 || p.epi_stg || p.xbox != BK || p.ybox != 128;
+  return ext ? launch_pw_ext<MB, BN, true>(tw, tx, tx4, ty, p, st) : launch_pw_ext<MB, BN, false>(tw, tx, tx4, ty, p, st);
 }
 
 int make_act_tmap(CUtensorMap* m, const void* base, int P, int Cc, int N, int box_rows) {
@@ -557,7 +569,7 @@ int run_conv_tc(const TcConv& c, const __nv_bfloat16* x, const __nv_bfloat16* bi
   const char* box5_env = env_get("SPC_PW_BOX5");
   const int box5 = box5_env ? atoi(box5_env) : ((size_t)P * 2 >= ((size_t)4 << 20) ? 3 : 0);
   const int x5 = (taps == 1 && cs == 1 && (box5 & 1) && P % 64 == 0 && c.Cin % 8 == 0 && xbox == BK) ? 1 : 0;
-  const int y5 = (taps == 1 && (box5 & 2) && P % 64 == 0 && c.M % 8 == 0 && ybox == 128) ? 1 : 0;   // (tap mode: the stem got slower)
+  const int y5 = (taps == 1 && (box5 & 2) && P % 64 == 0 && c.M % 8 == 0 && ybox == 128) ? 1 : 0;
   {
     const uint64_t dims[2] = {(uint64_t)Cpad, (uint64_t)taps * Mpad};
     const uint64_t strides[2] = {0, (uint64_t)Cpad * 2};
