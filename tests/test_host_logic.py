@@ -105,7 +105,7 @@ def test_dropin_import_shim_resolves_reference_imports():
         "from torchgems.gems_master import train_model_master\n"
         "import torchgems.comm as gems_comm\n"
         "from torchgems.spatial import conv_spatial, halo_exchange_layer, Pool\n"
-        "from models import resnet, resnet_spatial, amoebanet\n"
+        "from models import resnet, resnet_spatial, amoebanet, amoebanet_d2, resnet_spatial_d2\n"
         "from utils import get_depth, isPowerTwo\n"
         "import mpi4dl_b200.torchgems.train_spatial as mine\n"
         "assert train_model_spatial is mine.train_model_spatial and gems_comm.MPIComm.__module__.startswith('mpi4dl_b200')\n"
