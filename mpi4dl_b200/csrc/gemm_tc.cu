@@ -6,13 +6,18 @@
 //     dgrad : dX[C x P] = W^T[C x K] * dY[K x P]
 //     wgrad : dW[K x C] = dY[K x P] * X[C x P]^T       (reduction over pixels)
 // fprop/dgrad: A = (padded) weights, K-major, TMA box {64 ch, 128 rows}, SWIZZLE_128B;
-//              B = activations read IN PLACE by TMA as an MN-major operand: box {64 px, 64 ch}
-//              -> smem [ch][64 px] (128 B rows, SWIZZLE_128B); accumulator D[128 out-ch x BN px]
-//              lives in TMEM.  The epilogue thread that owns TMEM lane k holds BN consecutive
-//              pixels of output channel k, i.e. a contiguous NCHW run -> 16-byte stores.
+//              B = activations read IN PLACE by TMA as an MN-major operand: [ch][64 px] rows of 128 B,
+//              SWIZZLE_128B; accumulator D[128 out-ch x BN px] lives in TMEM.  The epilogue goes
+//              TMEM -> registers -> swizzled staging block in smem -> TMA store.
 // wgrad:       both operands K-major straight from NCHW (pixels = reduction dim, contiguous).
+// Box shapes:  a [64 ch][64 px] box touches 64 channel planes = 64 different 2 MB pages, and with plane strides
+//              of 8..32 MB they alias in the translation cache: every 128 bytes cost a page walk (4.3 TB/s
+//              ceiling, DESIGN.md "Address translation").  Layers with multi-page planes therefore move ONE
+//              5-d box per stage, dims (64 px, 8 ch, P/64 px blocks, C/8 ch groups, image): the TMA unit walks
+//              8 planes at a time and visits all pixel blocks of each before moving on; smem layout
+//              [group][block][8 ch][128 B], which the UMMA descriptors express through LBO / SBO.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
-// warps 2..5 = epilogue (TMEM -> registers -> global).  Persistent CTAs, one per SM.
+// warps 2..5 = epilogue.  Persistent CTAs, one per SM (wgrad for >= 400 input channels: CTA pairs, cta_group::2).
 #include <stdlib.h>
 
 #include "common.cuh"
