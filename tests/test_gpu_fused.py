@@ -37,7 +37,7 @@ def test_bn_relu_matches_batchnorm2d(shape, relu, dtype, tol):
     zb.backward(g)
 
     def close(a, b, name):
-        a, b = a.float(), b.float()
+        a, b = a.detach().float(), b.detach().float()
         scale = float(b.abs().max()) + 1e-6
         assert float((a - b).abs().max()) <= tol * scale, (name, float((a - b).abs().max()), scale)
 
