@@ -1,22 +1,21 @@
 #!/bin/bash
-# First GPU call of the next session (one B200, ~4 minutes): what round 1 could not measure any more.
-#   gpurun --timeout 600 -- 'bash tools/next_gpu_session.sh'
-# 1. the cta_group::2 wgrad pair kernel, never run on hardware yet (outer timeout: a hang must not take the box)
-# 2. the single-CTA wgrad tiling sweep
-# 3. the full GPU test suite + the default bench line
+# What the round-2 GPU budget no longer covered, in the order it should be measured (one B200 unless noted):
+#   gpurun --timeout 900 -- 'bash tools/next_gpu_session.sh'
+# 1. wide wgrad stages / 5-d boxes BELOW their default thresholds (1 MB and 512 KB planes = the 1024^2-level layers at
+#    N=2 / N=4, where the default falls back to 3-d boxes): SPC_WG_WIDE=1 SPC_WG_PAIR_WIDE=1 SPC_PW_BOX5=3 on tile shapes
+#    of N=2/4/8 (tools/halo_cost_probe.py N prints fprop / wgrad per halo layer; tools/wgrad_probe.py takes square shapes)
+# 2. bench at N=8 with the final binary (gpurun --gpus 8 -- 'bash tools/gpu_multi_bench_only.sh 8'); round 2's last N=8
+#    record (27.9 ms) predates the 5-d boxes
+# 3. ncu --set full of the wide pair wgrad and of pw_gemm with 5-d boxes (dram bytes, translation stalls) -> profiles/
+# 4. next kernels: CTA-pair (cta_group::2) fprop/dgrad for the 1024^2 compute-heavy layers (they are L2->SM bound on
+#    re-streamed weights, DESIGN.md "Address translation"); a 4-row tail box so that 52-channel operands can use 5-d boxes;
+#    a small-C stem kernel; kind::tf32 for fp32 storage
 mkdir -p gpurun_out
-timeout 90 python tools/wgrad_probe.py --pair --quick > gpurun_out/wgrad_pair.log 2>&1; echo "pair probe rc=$?"
-tail -12 gpurun_out/wgrad_pair.log
-timeout 240 python tools/wgrad_probe.py > gpurun_out/wgrad_sweep.log 2>&1; echo "sweep rc=$?"
-timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/tests_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/tests_gpu.log
-timeout 200 python bench.py --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
-python -c "import json;d=json.load(open('gpurun_out/bench_n1.json'));print(d['ms_per_step'],d['value'],d['e2e']['value'])"
-# 4. the self-checking halo benchmarks (reference's own validation tools), 4 tiles sharing the GPU over gloo
-export SPCONV_DIST_BACKEND=gloo
-for m in vertical square; do
-  timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29661 \
-    benchmarks/communication/halo/benchmark_sp_halo_exchange_conv.py --image-size 64 --halo-len 3 --num-spatial-parts 4 \
-    --slice-method $m --in-channels 2 --out-channels 8 --iterations 10 --enable-val-recv-tensors --enable-val-conv 2>&1 | grep "Rank:"
+for n in 2 4 8; do
+  echo "== tile shapes of N=$n, defaults"; timeout 120 python tools/halo_cost_probe.py $n | tail -1
+  echo "== tile shapes of N=$n, wide / 5-d forced"; SPC_WG_WIDE=1 SPC_WG_PAIR_WIDE=1 SPC_PW_BOX5=3 timeout 120 python tools/halo_cost_probe.py $n | tail -1
 done
-timeout 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29662 \
-  benchmarks/communication/halo/benchmark_sp_halo_exchange.py --image-size 32 --halo-len 2 --num-spatial-parts 2 --slice-method horizontal 2>&1 | grep "Rank:"
+timeout 200 python tools/wgrad_probe.py --wide > gpurun_out/wgrad_wide.log 2>&1; tail -30 gpurun_out/wgrad_wide.log
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/tests_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/tests_gpu.log
+timeout 300 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"
+python -c "import json;d=json.load(open('gpurun_out/bench_n1.json'));print(d['ms_per_step'],d['value'],d['e2e']['value'])"
