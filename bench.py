@@ -194,7 +194,10 @@ def run_reference(args):
     d, desc = load_layers(args.workload)
     steps = max(1, args.steps)
     # whole run (calibration + warm-up + K timed passes) bounded to ~2-3 minutes on a 16-CPU container
-    cores, scale, _ = cpu_reference_setup(d["layers"], args.cpu_scale, budget_s=min(12.0, 120.0 / (steps + max(1, args.warmup))))
+    budget = min(12.0, 120.0 / (steps + max(1, args.warmup)))
+    if os.environ.get("SPCONV_BENCH_CPU_BUDGET_S"):          # tests: a smaller sample
+        budget = float(os.environ["SPCONV_BENCH_CPU_BUDGET_S"])
+    cores, scale, _ = cpu_reference_setup(d["layers"], args.cpu_scale, budget_s=budget)
     for _ in range(max(0, args.warmup - 1)):         # (cpu_reference_setup already ran one warm pass at this size)
         rp.run_workload(d["layers"], scale, warm=False)
     times = [rp.run_workload(d["layers"], scale, warm=False) for _ in range(steps)]

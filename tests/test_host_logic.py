@@ -142,3 +142,27 @@ def test_halo_benchmark_known_answers_match_the_oracle():
             for r in range(P):
                 assert np.array_equal(hc.expected_conv_tile(full, method, P, r, kh, kw, 4), ref[r]["y"].astype(np.float64)), \
                     (method, P, kh, kw, r)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's second arm): one JSON line with the contract's keys, produced on the
+    host by the oracle port alone; under torchrun only rank 0 prints, the other ranks exit 0 without work."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", SPCONV_BENCH_CPU_BUDGET_S="0.01")
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-scale", "128"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/sec" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["value"] > 0 and "8192" in d["config"]["workload"] and d["vs_baseline"] is None
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=120, cwd=root,
+                           env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert other.returncode == 0 and other.stdout.strip() == "", (other.stdout, other.stderr[-500:])
